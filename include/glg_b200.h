@@ -1,0 +1,200 @@
+/*
+ * glg_b200.h - C ABI of the B200-native batched Race / Pacman environment kernels.
+ *
+ * This is the drop-in boundary of the hot path: every entry point takes
+ * plain DEVICE pointers, extents and a CUDA stream; nothing here allocates, synchronises or
+ * touches the host side of a tensor.  The caller (PyTorch, through ctypes - see
+ * game_level_gan_b200/_lib.py and INTEGRATION.md) owns every buffer.
+ *
+ * All functions return GLG_OK (0) or a negative error code; glg_last_error() gives the text.
+ * All functions are re-entrant; there is no global state besides the thread-local error string.
+ *
+ * File:line citations name the interface of the reference (Grzego/game-level-gan) that an entry
+ * point replaces; they are relative to the reference's repository root.
+ */
+#ifndef GLG_B200_H
+#define GLG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLG_OK            0
+#define GLG_ERR_ARG      -1   /* bad argument (null pointer, extent out of range, misalignment) */
+#define GLG_ERR_LAUNCH   -2   /* cudaGetLastError() after a launch was not cudaSuccess        */
+#define GLG_ERR_UNSUPPORTED -3
+
+#define GLG_MAX_PLAYERS   8
+#define GLG_MAX_RAYS      32
+#define GLG_ALIVE_SLOTS   64  /* int32 slots of the "somebody is alive" step stamp            */
+
+/* step kernel variants (all produce identical results; tests compare them) */
+#define GLG_STEP_FAST     0   /* exact angular pruning of the ray cast (production)            */
+#define GLG_STEP_BRUTE    1   /* every ray x every wall, the literal reference loop            */
+
+typedef void* glg_stream_t;   /* cudaStream_t */
+
+const char* glg_last_error(void);
+int glg_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Simulation constants of one Race instance.  Replaces the tensors built in
+ * games/race.py:26-82 (Race.__init__: car tables, action tables, observation setup).
+ *
+ * The trigonometric entries are computed ON THE HOST WITH TORCH by the caller, using the same
+ * ops the reference uses per step (games/race.py:310-324, 362-363, 462-466), so that headings and
+ * ray directions are bit-identical to the reference; the kernels never call sinf/cosf per step.
+ * Index f of the steering tables: 0 = straight, 1 = action_dirs +1 (right), 2 = action_dirs -1.
+ * Index f of speed_inc: 0 = action_speed 0, 1 = +1 (forward), 2 = -3 (brake).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct glg_race_params {
+    int32_t num_players;                       /* P, 1..GLG_MAX_PLAYERS                        */
+    int32_t num_rays;                          /* observation_size, 1..GLG_MAX_RAYS            */
+    int32_t steps_limit;                       /* int(timeout // framerate), race.py:47        */
+    float   max_distance;                      /* race.py:26 (10.)                             */
+    float   step_penalty;                      /* race.py:74 (-0.01)                           */
+    float   drag;                              /* race.py:346 (0.05)                           */
+    float   progress_div;                      /* race.py:376: bounds.size(2) - 1 == 3         */
+    float   vmax[GLG_MAX_PLAYERS];             /* race.py:34                                   */
+    float   speed_inc[GLG_MAX_PLAYERS][3];     /* fl(fl(framerate*flag)*accel), race.py:367    */
+    float   turn_cos[GLG_MAX_PLAYERS][3];      /* cos/sin of framerate*flag*angle, race.py:363 */
+    float   turn_sin[GLG_MAX_PLAYERS][3];
+    float   ray_cos[GLG_MAX_RAYS];             /* cos/sin of torch.linspace(...), race.py:462  */
+    float   ray_sin[GLG_MAX_RAYS];
+} glg_race_params;
+
+/* Per-car state, structure of arrays, each array in the reference's own tensor layout
+ * (games/race.py:182-190), so the host wrapper exposes them as Race.positions, .alive, ...  */
+typedef struct glg_race_state {
+    float*   positions;    /* [B,P,2] f32 */
+    float*   directions;   /* [B,P,2] f32 */
+    float*   speeds;       /* [B,P]   f32 */
+    uint8_t* alive;        /* [B,P]   bool */
+    uint8_t* finishes;     /* [B,P]   bool */
+    int32_t* scores;       /* [B,P]   i32 */
+} glg_race_state;
+
+/* ------------------------------------------------------------------------------------------
+ * Track geometry in HBM: one contiguous record per track,
+ *     geom[b] = { right[N] , left[N] , centre[N] }  each point (x,y) f32,   N = L + 2,
+ * i.e. a [B,3,N,2] f32 tensor (3*N*8 bytes per track = 3120 B at L = 128, 16-byte aligned so the
+ * step kernel can stage a record with one bulk async copy).  Walls, start and finish lines are
+ * derived from consecutive points on the fly; the reference's per-player duplicated
+ * `bounds [B*P,2L+3,4]` (race.py:172-173) is never materialised on the hot path.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Generator output -> geometry.  Replaces games/race.py:126-158 (Race.reset, geometry part).
+ *   tracks     [B,L,2] f32 (arc, width)
+ *   sin_table / cos_table: optional [2*table_half+1] host-torch values of sin/cos(fl32(rad 8deg)*(n/4)),
+ *              n = -table_half..table_half.  Tracks whose arcs are all exact multiples of 0.25
+ *              (every generator-produced track) then get headings bit-identical to the reference;
+ *              other tracks (or NULL tables) use sinf/cosf (<= 2 ulp from the reference's SLEEF).
+ *   geom       [B,3,N,2] f32 out                                                             */
+int glg_track_build(const float* tracks, int32_t B, int32_t L,
+                    const float* sin_table, const float* cos_table, int32_t table_half,
+                    float* geom, glg_stream_t stream);
+
+/* Track validity = no proper crossing among the 2(L+1)+2 lines (walls, start, finish).
+ * Replaces Race._is_correct, games/race.py:326-334 (IMPL_GPU branch of reset, :199-200).
+ *   valid [B] u8 out                                                                         */
+int glg_track_validate(const float* geom, int32_t B, int32_t N, uint8_t* valid, glg_stream_t stream);
+
+/* Initial car state (games/race.py:182-190) and a cleared alive stamp.                        */
+int glg_race_init(glg_race_state state, int32_t B, int32_t P, int32_t* alive_stamp, glg_stream_t stream);
+
+/* One environment step for every car.  Replaces Race.step, games/race.py:340-500 (IMPL_GPU):
+ * action masking, kinematics, progress, wall/finish collision, reward, score, drag, 18-ray
+ * sensors, observation pack.
+ *   actions    [P,B] i64 (values 0..8), not modified
+ *   valid      [B] u8 (per track)
+ *   step_no    value of Race.steps AFTER the increment of this step (race.py:349)
+ *   states_out [P,B,num_rays+2] f32, rewards_out [P,B] f32
+ *   alive_stamp [GLG_ALIVE_SLOTS] i32 or NULL: slot (b % 64) := step_no if track b still has an
+ *              alive car after this step (host reads it for Race.finished(), race.py:502-504)
+ *   history    optional [>= step_no+1, P, 6] f32 ring written for track `record_id`
+ *              (x, y, dx, dy, masked action, alive) at row step_no (race.py:492-494), or NULL
+ *   variant    GLG_STEP_FAST or GLG_STEP_BRUTE                                                */
+int glg_race_step(const glg_race_params* params, const float* geom, int32_t B, int32_t N,
+                  const int64_t* actions, const uint8_t* valid, glg_race_state state,
+                  int32_t step_no, float* states_out, float* rewards_out,
+                  int32_t* alive_stamp, float* history, int32_t record_id,
+                  int32_t variant, glg_stream_t stream);
+
+/* T consecutive steps with pre-computed actions [T,P,B] (random-action rollouts, replay).
+ * Launches T step kernels back to back on `stream`; states_out/rewards_out hold the LAST step's
+ * outputs, or all steps if `keep_all` (then [T,P,B,W] / [T,P,B]).  first_step_no as in glg_race_step. */
+int glg_race_rollout(const glg_race_params* params, const float* geom, int32_t B, int32_t N,
+                     const int64_t* actions, int32_t T, const uint8_t* valid, glg_race_state state,
+                     int32_t first_step_no, float* states_out, float* rewards_out, int32_t keep_all,
+                     int32_t* alive_stamp, int32_t variant, glg_stream_t stream);
+
+/* Winner per track.  Replaces Race.winners, games/race.py:506-529.  winners [B] i64 out.      */
+int glg_race_winners(const int32_t* scores, const uint8_t* finishes, const uint8_t* valid,
+                     int32_t B, int32_t P, int32_t steps_limit, int64_t* winners, glg_stream_t stream);
+
+/* Winner statistics for the winner discriminator (train-gan.py:103-104): tracks are laid out
+ * trial-major [trials, boards]; out[board, c] = mean over trials of one_hot(winner+1, P+1).
+ *   winners [trials*boards] i64, out [boards, P+1] f32                                        */
+int glg_winner_stats(const int64_t* winners, int32_t trials, int32_t boards, int32_t P,
+                     float* out, glg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stateless helpers.  Replace the three free functions of the pybind module `game_helpers`
+ * (games/game_helpers.cpp:335-371, 373-418, 421-450; bound at :455-457).  The reference backs
+ * them with Boost.Geometry (not vendored, unpinned); semantics here: intersection including
+ * touches, Euclidean distance from the ray origin to the nearest intersection point (+inf if
+ * none), validity = the polyline does not intersect itself.
+ * ------------------------------------------------------------------------------------------ */
+/* tracks [b,s,2] f32 polyline, segments [b,p,4] f32, out [b,p] u8 */
+int glg_collision(const float* tracks, const float* segments, uint8_t* out,
+                  int32_t b, int32_t s, int32_t p, glg_stream_t stream);
+/* tracks [b,s,2], directions [b,d,4] = (x,y,dx,dy), out [b,d] f32 */
+int glg_smallest_distance(const float* tracks, const float* directions, float* out,
+                          int32_t b, int32_t s, int32_t d, glg_stream_t stream);
+/* tracks [b,s,2], out [b] u8 */
+int glg_is_valid(const float* tracks, uint8_t* out, int32_t b, int32_t s, glg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stateful helper.  Replaces class `Game` of the pybind module (games/game_helpers.cpp:158-327,
+ * bound at :459-463): per-player cell tracking along the track.
+ * The handle is a small host object; all device storage lives in a caller-provided workspace of
+ * glg_game_workspace_bytes(b, s, num_players) bytes (256-byte aligned device memory).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct glg_game glg_game;
+
+int64_t glg_game_workspace_bytes(int32_t b, int32_t s, int32_t num_players);
+/* left,right [b,s,2] f32 device.  Copies them into the workspace in the order of
+ * create_racetracks (game_helpers.cpp:109-144) and initialises players (:146-156, 160-174).   */
+int glg_game_create(glg_game** out, void* workspace, int64_t workspace_bytes,
+                    const float* left, const float* right, int32_t b, int32_t s,
+                    int32_t num_players, glg_stream_t stream);
+void glg_game_destroy(glg_game* game);
+/* game_helpers.cpp:176-189.  valid [b] u8 out. */
+int glg_game_validate_tracks(glg_game* game, uint8_t* valid, glg_stream_t stream);
+/* game_helpers.cpp:191-279.  idx [k] i64, new_positions [k,row_stride] f32 (columns 0,1 used),
+ * dead/finished [k] u8 out.  Mutates the players' position/cell.                              */
+int glg_game_update_players(glg_game* game, const int64_t* idx, const float* new_positions,
+                            int32_t k, int32_t row_stride, uint8_t* dead, uint8_t* finished,
+                            glg_stream_t stream);
+/* game_helpers.cpp:281-322.  idx [k] i64, directions [k,d,4] f32, out [k,d] f32.               */
+int glg_game_smallest_distance(glg_game* game, const int64_t* idx, const float* directions,
+                               int32_t k, int32_t d, float* out, glg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Pacman grid environment.  Replaces Pacman.step / observation build, games/pacman.py:64-109.
+ *   grid    [B,H,W,4+P] i32 (the 4+P "real" channels of the reference's [B,H,W,4+2P] grid)
+ *   players [B*P,4] i32 rows (b,x,y,p) in the reference's np.where order (pacman.py:59-61)
+ *   actions [B,P] i32 (0..4), rewards [P,B] f64 out (the reference returns float64 rewards)
+ * ------------------------------------------------------------------------------------------ */
+int glg_pacman_step(int32_t* grid, int32_t* players, const int32_t* actions, double* rewards,
+                    int32_t B, int32_t H, int32_t W, int32_t P, glg_stream_t stream);
+/* obs [P,B,H,W,4+2P] f32 out: grid channels, zeros, and 1.0 in channel 4+P+p (pacman.py:107-109) */
+int glg_pacman_observe(const int32_t* grid, float* obs, int32_t B, int32_t H, int32_t W, int32_t P,
+                       glg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLG_B200_H */
