@@ -1,0 +1,177 @@
+// glg_track.cu - generator output -> track geometry, and track validity (sm_100a).
+//
+//   glg_track_build    replaces games/race.py:126-158  (Race.reset, geometry part)
+//   glg_track_validate replaces games/race.py:326-334  (Race._is_correct) as used at :199-200
+//
+// HBM layout of the result: one record {right[N], left[N], centre[N]} of float2 per track
+// (include/glg_b200.h).  Both kernels are "reset-time" work, amortised over hundreds of steps.
+#include <math.h>
+
+#include "glg_common.cuh"
+#include "glg_exact.cuh"
+
+namespace glg {
+
+constexpr int BUILD_WARPS = 4;
+
+// One warp per track.  The two prefix sums replicate ATen's CPU cumsum bit-for-bit: a sequential
+// running sum in double, every prefix rounded to float - therefore one lane walks
+// the 130 elements; everything else (sin/cos, normals, offsets, stores) is lane-parallel.
+__global__ void __launch_bounds__(BUILD_WARPS * 32)
+track_build_kernel(const float* __restrict__ tracks, int B, int L,
+                   const float* __restrict__ sin_table, const float* __restrict__ cos_table,
+                   int table_half, float* __restrict__ geom)
+{
+    extern __shared__ float smem[];
+    const int N = L + 2;
+    const int lane = lane_id();
+    const int wib = threadIdx.x >> 5;
+    const int b = blockIdx.x * BUILD_WARPS + wib;
+    if (b >= B) return;                                   // whole warp leaves together
+    float* head = smem + wib * 5 * N;                     // [N] heading prefix (in arc units)
+    float2* seg = reinterpret_cast<float2*>(head + N);    // [N] segment vectors
+    float2* cen = seg + N;                                // [N] centre points
+    const float2* trk = reinterpret_cast<const float2*>(tracks) + (size_t)b * L;
+
+    // sentinels (race.py:136-138) + "all arcs are multiples of 1/4" test for the table path
+    bool quant = sin_table != nullptr;
+    for (int j = lane; j < N; j += 32) {
+        const float arc = (j >= 1 && j <= L) ? __ldg(&trk[j - 1]).x : 0.f;
+        head[j] = arc;
+        const float a4 = arc * 4.f;
+        if (a4 != rintf(a4) || fabsf(a4) > 4.f) quant = false;
+    }
+    quant = __all_sync(FULL, quant);
+    __syncwarp();
+    if (lane == 0) {                                      // race.py:140 cumsum (double accumulator)
+        double acc = 0.0;
+        for (int j = 0; j < N; ++j) {
+            acc += (double)head[j];
+            head[j] = (float)acc;
+        }
+    }
+    __syncwarp();
+    const float rad8 = (float)0.13962634015954636;        // math.radians(8.) as an fp32 scalar
+    for (int j = lane; j < N; j += 32) {                  // race.py:140-142
+        const float h = head[j];
+        const float ang = xmul(rad8, h);
+        const int n = (int)(h * 4.f);
+        float s, c;
+        if (quant && n >= -table_half && n <= table_half) {
+            s = __ldg(&sin_table[n + table_half]);
+            c = __ldg(&cos_table[n + table_half]);
+        } else {
+            s = sinf(ang);
+            c = cosf(ang);
+        }
+        seg[j] = make_float2(xmul(s, 0.2f), xmul(c, 0.2f));
+    }
+    __syncwarp();
+    if (lane < 2) {                                       // race.py:154-156 exclusive cumsum, x and y
+        double acc = 0.0;
+        float* dst = reinterpret_cast<float*>(cen) + lane;
+        const float* src = reinterpret_cast<const float*>(seg) + lane;
+        for (int j = 0; j < N; ++j) {
+            dst[2 * j] = (float)acc;
+            acc += (double)src[2 * j];
+        }
+    }
+    __syncwarp();
+    float2* rec = reinterpret_cast<float2*>(geom) + (size_t)b * 3 * N;
+    for (int j = lane; j < N; j += 32) {                  // race.py:144-152, 157-158
+        float ox = 0.5f, oy = 0.f;
+        if (j > 0) {
+            const float2 s1 = seg[j], s0 = seg[j - 1];
+            const float nx = xadd(s1.y, s0.y);            // perp = (y, -x)
+            const float ny = xadd(-s1.x, -s0.x);
+            const float len = norm2(nx, ny);
+            const float wid = (j >= 2 && j - 1 <= L) ? __ldg(&trk[j - 2]).y : 0.f;
+            const float w = xadd(0.5f, xmul(1.5f, wid));
+            ox = xmul(xdiv(nx, len), w);
+            oy = xmul(xdiv(ny, len), w);
+        }
+        const float2 c = cen[j];
+        rec[j] = make_float2(xadd(c.x, ox), xadd(c.y, oy));              // right
+        rec[N + j] = make_float2(xadd(c.x, -ox), xadd(c.y, -oy));        // left
+        rec[2 * N + j] = c;                                              // centre
+    }
+}
+
+// One CTA per track; the M = 2(N-1)+2 lines live in shared memory and every unordered pair is
+// tested once ((o1*o2<0)&(o3*o4<0) is symmetric in the pair).  Rows i and M-1-i are folded into
+// one work item so that every thread runs M-1 pair tests.
+__global__ void track_validate_kernel(const float* __restrict__ geom, int B, int N,
+                                      uint8_t* __restrict__ valid)
+{
+    extern __shared__ float4 lines[];
+    __shared__ int bad_flag;
+    const int b = blockIdx.x;
+    const int S = N - 1;
+    const int M = 2 * S + 2;
+    const float2* rec = reinterpret_cast<const float2*>(geom) + (size_t)b * 3 * N;
+    if (threadIdx.x == 0) bad_flag = 0;
+    for (int j = threadIdx.x; j < M; j += blockDim.x) {   // race.py:166-172 + finish line :169
+        float2 p, q;
+        if (j < S) { p = rec[j]; q = rec[j + 1]; }
+        else if (j < 2 * S) { p = rec[N + j - S]; q = rec[N + j - S + 1]; }
+        else if (j == 2 * S) { p = rec[N]; q = rec[0]; }
+        else { p = rec[N + N - 1]; q = rec[N - 1]; }
+        lines[j] = make_float4(p.x, p.y, q.x, q.y);
+    }
+    __syncthreads();
+    const int half = M / 2;
+    for (int w = threadIdx.x; w < half; w += blockDim.x) {
+        const int first = M - 1 - w;                       // pairs in row w; the rest go to row M-1-w
+        int i = w;
+        float4 a = lines[i];
+        for (int m = 0; m < M - 1; ++m) {
+            int j;
+            if (m < first) j = w + 1 + m;
+            else {
+                if (m == first) { i = M - 1 - w; a = lines[i]; }
+                j = i + 1 + (m - first);
+            }
+            const float4 c = lines[j];
+            const P2 ap{a.x, a.y}, aq{a.z, a.w}, cp{c.x, c.y}, cq{c.z, c.w};
+            const int o1 = turn(ap, aq, cp), o2 = turn(ap, aq, cq);
+            const int o3 = turn(cp, cq, ap), o4 = turn(cp, cq, aq);
+            if (o1 * o2 < 0 && o3 * o4 < 0) bad_flag = 1;
+            if ((m & 63) == 63 && bad_flag) break;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) valid[b] = bad_flag ? 0 : 1;
+}
+
+}  // namespace glg
+
+extern "C" int glg_track_build(const float* tracks, int32_t B, int32_t L, const float* sin_table,
+                               const float* cos_table, int32_t table_half, float* geom,
+                               glg_stream_t stream)
+{
+    using namespace glg;
+    GLG_REQUIRE(B >= 0 && L >= 1 && L <= 510, "glg_track_build: need B >= 0 and 1 <= L <= 510 (got B=%d L=%d)", B, L);
+    GLG_REQUIRE((B == 0) || (tracks && geom), "glg_track_build: null pointer");
+    GLG_REQUIRE((sin_table == nullptr) == (cos_table == nullptr), "glg_track_build: give both tables or none");
+    if (B == 0) return GLG_OK;
+    const int N = L + 2;
+    const size_t smem = (size_t)BUILD_WARPS * 5 * N * sizeof(float);
+    const int grid = (B + BUILD_WARPS - 1) / BUILD_WARPS;
+    track_build_kernel<<<grid, BUILD_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        tracks, B, L, sin_table, cos_table, table_half, geom);
+    return launch_status("glg_track_build");
+}
+
+extern "C" int glg_track_validate(const float* geom, int32_t B, int32_t N, uint8_t* valid,
+                                  glg_stream_t stream)
+{
+    using namespace glg;
+    GLG_REQUIRE(B >= 0 && N >= 2 && N <= 512, "glg_track_validate: need B >= 0 and 2 <= N <= 512 (got B=%d N=%d)", B, N);
+    GLG_REQUIRE((B == 0) || (geom && valid), "glg_track_validate: null pointer");
+    if (B == 0) return GLG_OK;
+    const int M = 2 * (N - 1) + 2;
+    int threads = ((M / 2 + 31) / 32) * 32;
+    if (threads > 1024) threads = 1024;
+    track_validate_kernel<<<B, threads, (size_t)M * sizeof(float4), (cudaStream_t)stream>>>(geom, B, N, valid);
+    return launch_status("glg_track_validate");
+}

@@ -1,0 +1,323 @@
+"""Drop-in `Race` environment backed by the sm_100a kernels (replaces games/race.py:9-529, 920-928).
+
+Same constructor, methods, public attributes, shapes and dtypes as the reference class; tensors live
+on the environment's CUDA device.  All work of `reset` / `step` / `winners` happens in
+game_level_gan_b200/csrc (one fused kernel per step) through the C ABI of include/glg_b200.h.
+Semantics are those of the reference's torch path (IMPL_GPU) - the only one that can run without
+Boost - including its quirks.  There is no CPU fallback.
+
+Host synchronisation: `step` launches one kernel and returns; the Python control flow the API needs
+(`any_valid` from `reset`, `finished()`, the "nobody alive" early-out of `step`) reads a 256-byte
+step stamp the kernel maintains, at most once per step and only when asked.
+"""
+import math
+
+import torch
+
+from .. import _lib
+from .._lib import GlgError, RaceState, check, ptr
+from . import _tables
+from .environment import MultiEnvironment
+
+
+class RaceCar(object):
+    """Car description in the reference's units (games/race.py:9-18)."""
+
+    def __init__(self, max_speed, acceleration, angle):
+        # km/h -> units/s (1 unit = 10 m), m/s^2 -> units/s^2, degrees/s -> rad/s
+        self.max_speed = max_speed * 100. / 3600.
+        self.acceleration = acceleration * 0.1
+        self.angle = angle * math.pi / 180.
+
+
+def _default_device():
+    if not torch.cuda.is_available():
+        return None
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+class Race(MultiEnvironment):
+    IMPL_BOOST = 0
+    IMPL_GPU = 1
+    IMPL_CPP = 2
+    IMPL_B200 = 3
+
+    ACTION_NAMES = ('noop', 'forward', 'backward', 'right', 'forward-right', 'backward-right',
+                    'left', 'forward-left', 'backward-left')
+
+    def __init__(self, timeout, cars, observation_size=18, max_distance=10., framerate=1. / 30.,
+                 log_history=True, device=None, variant='fast'):
+        self._device = torch.device(device) if device is not None else None
+        if self._device is not None and self._device.type != 'cuda':
+            raise GlgError('Race runs on CUDA devices only (got %s); there is no CPU fallback' % self._device)
+        self.timeout = timeout
+        self.framerate = framerate
+        self.cars = list(cars)
+        self.num_players = len(self.cars)
+        self.num_tracks = None
+        self.steps = 0
+        self.steps_limit = int(timeout // framerate)
+        self.observation_size = observation_size
+        self.max_distance = max_distance
+        self.negative_reward = -0.01
+        self.log_history = log_history
+        self.record_id = 0
+        self.game_handle = None
+        self._impl_version = Race.IMPL_B200
+        self.variant = variant
+        self._params = _tables.race_params(self.cars, framerate, timeout, observation_size, max_distance,
+                                           step_penalty=self.negative_reward)
+        self._const = {}
+        self._geom = None
+        self._alive_known = None
+        self._hist_steps = []
+        self._hist = None
+        self.positions = self.directions = self.speeds = None
+        self._alive = self._finishes = self.scores = None
+        self._valid_tracks = None
+
+    # ---- device / constants --------------------------------------------------------------------
+    @property
+    def device(self):
+        if self._device is None:
+            self._device = _default_device()
+            if self._device is None:
+                raise GlgError('no CUDA device available; game_level_gan_b200 has no CPU fallback')
+        return self._device
+
+    def _constant(self, name, values):
+        if name not in self._const:
+            self._const[name] = torch.tensor(values, dtype=torch.float32, device=self.device)
+        return self._const[name]
+
+    cars_max_speed = property(lambda self: self._constant('vmax', [c.max_speed for c in self.cars]))
+    cars_acceleration = property(lambda self: self._constant('acc', [c.acceleration for c in self.cars]))
+    cars_angle = property(lambda self: self._constant('ang', [c.angle for c in self.cars]))
+    action_speed = property(lambda self: self._constant('aspeed', [0., 1., -3.] * 3))
+    action_dirs = property(lambda self: self._constant('adirs', [0.] * 3 + [1.] * 3 + [-1.] * 3))
+
+    def _heading_tables(self, L):
+        key = ('heading', L)
+        if key not in self._const:
+            s, c, half = _tables.heading_tables(L)
+            self._const[key] = (s.to(self.device), c.to(self.device), half)
+        return self._const[key]
+
+    def _variant_code(self):
+        return {'fast': _lib.STEP_FAST, 'brute': _lib.STEP_BRUTE}[self.variant]
+
+    # ---- reference API -------------------------------------------------------------------------
+    def state_shape(self):
+        return self.observation_size + 2,
+
+    def players_layer_shape(self):
+        pass
+
+    def record(self, board):
+        self.record_id = board
+
+    def change_timeout(self, timeout):
+        self.timeout = timeout
+        self.steps_limit = int(timeout // self.framerate)
+        self._params.steps_limit = self.steps_limit
+
+    @property
+    def actions(self):
+        return 9
+
+    @staticmethod
+    def action_name(a):
+        return Race.ACTION_NAMES[a]
+
+    def reset(self, tracks, geometry=None):
+        """tracks [B, L, (arc, width)] -> (states [P,B,O+2], any_valid).  games/race.py:116-211.
+
+        `geometry=(centre, left, right)` ([B,L+2,2] each) skips the build and uses the given
+        polylines instead (parity tests isolate step parity from build parity this way).
+        """
+        dev = self.device
+        lib = _lib.lib()
+        stream = _lib.stream_ptr(dev)
+        with torch.no_grad():
+            tracks = tracks.detach().to(device=dev, dtype=torch.float32).contiguous()
+            B, L = tracks.size(0), tracks.size(1)
+            N, P = L + 2, self.num_players
+            self.steps = 0
+            self.num_tracks = B
+            self._lazy = {}
+            self._geom = torch.empty((B, 3, N, 2), dtype=torch.float32, device=dev)
+            if geometry is not None:
+                centre, left, right = (g.to(device=dev, dtype=torch.float32) for g in geometry)
+                self._geom[:, 0], self._geom[:, 1], self._geom[:, 2] = right, left, centre
+            else:
+                st, ct, half = self._heading_tables(L)
+                check(lib.glg_track_build(ptr(tracks), B, L, ptr(st), ptr(ct), half, ptr(self._geom), stream),
+                      'glg_track_build')
+            self._valid_tracks = torch.empty((B,), dtype=torch.uint8, device=dev)
+            check(lib.glg_track_validate(ptr(self._geom), B, N, ptr(self._valid_tracks), stream),
+                  'glg_track_validate')
+            self.positions = torch.empty((B, P, 2), dtype=torch.float32, device=dev)
+            self.directions = torch.empty((B, P, 2), dtype=torch.float32, device=dev)
+            self.speeds = torch.empty((B, P), dtype=torch.float32, device=dev)
+            self._alive = torch.empty((B, P), dtype=torch.uint8, device=dev)
+            self._finishes = torch.empty((B, P), dtype=torch.uint8, device=dev)
+            self.scores = torch.empty((B, P), dtype=torch.int32, device=dev)
+            self._stamp = torch.empty((_lib.ALIVE_SLOTS,), dtype=torch.int32, device=dev)
+            self._stamp_host = torch.zeros((_lib.ALIVE_SLOTS,), dtype=torch.int32).pin_memory()
+            self._state = RaceState(ptr(self.positions), ptr(self.directions), ptr(self.speeds),
+                                    ptr(self._alive), ptr(self._finishes), ptr(self.scores))
+            check(lib.glg_race_init(self._state, B, P, ptr(self._stamp), stream), 'glg_race_init')
+            self._alive_known = B * P > 0
+            self._hist_steps = []
+            self._hist = None
+            if self.log_history and B > 0:
+                self._hist = torch.zeros((self.steps_limit + 3, P, 6), dtype=torch.float32, device=dev)
+            any_valid = bool(self._valid_tracks.any().item()) if B > 0 else False
+            noop = torch.zeros((P, B), dtype=torch.int64, device=dev)
+            return self.step(noop)[0], any_valid
+
+    def step(self, actions):
+        """actions [P,B] int64 -> (states [P,B,O+2] f32, rewards [P,B] f32).  games/race.py:340-500."""
+        dev = self.device
+        with torch.no_grad():
+            B, P, O = self.num_tracks, self.num_players, self.observation_size
+            actions = actions.detach().to(device=dev, dtype=torch.int64).contiguous()
+            if tuple(actions.shape) != (P, B):
+                raise ValueError('actions must have shape [num_players, num_boards] = [%d, %d]' % (P, B))
+            self.steps += 1
+            if not self._any_alive():                      # games/race.py:353-356 (19-wide quirk)
+                states = torch.zeros((P, B, O + 1), dtype=torch.float32, device=dev)
+                rewards = (1. - self.finishes.float()) * self.negative_reward
+                return states, rewards.t()
+            states = torch.empty((P, B, O + 2), dtype=torch.float32, device=dev)
+            rewards = torch.empty((P, B), dtype=torch.float32, device=dev)
+            hist = None
+            if self._hist is not None and 0 <= self.record_id < B:
+                if self.steps >= self._hist.size(0):
+                    grown = torch.zeros((2 * self._hist.size(0), P, 6), dtype=torch.float32, device=dev)
+                    grown[:self._hist.size(0)] = self._hist
+                    self._hist = grown
+                hist = self._hist
+                self._hist_steps.append(self.steps)
+            check(_lib.lib().glg_race_step(
+                self._params, ptr(self._geom), B, self._geom.size(2), ptr(actions), ptr(self._valid_tracks),
+                self._state, self.steps, ptr(states), ptr(rewards), ptr(self._stamp), ptr(hist),
+                self.record_id, self._variant_code(), _lib.stream_ptr(dev)), 'glg_race_step')
+            self._alive_known = None
+            return states, rewards
+
+    def rollout(self, actions, keep_all=False):
+        """T steps with pre-computed actions [T,P,B] (no per-step host work).  Returns the outputs of
+        the last step, or of all steps ([T,P,B,O+2], [T,P,B]) with keep_all.  Equivalent to T calls of
+        `step` as long as somebody is alive throughout (the 19-wide early-out is not applied)."""
+        dev = self.device
+        with torch.no_grad():
+            actions = actions.detach().to(device=dev, dtype=torch.int64).contiguous()
+            T = actions.size(0)
+            B, P, O = self.num_tracks, self.num_players, self.observation_size
+            shape_s = (T, P, B, O + 2) if keep_all else (P, B, O + 2)
+            shape_r = (T, P, B) if keep_all else (P, B)
+            states = torch.empty(shape_s, dtype=torch.float32, device=dev)
+            rewards = torch.empty(shape_r, dtype=torch.float32, device=dev)
+            check(_lib.lib().glg_race_rollout(
+                self._params, ptr(self._geom), B, self._geom.size(2), ptr(actions), T, ptr(self._valid_tracks),
+                self._state, self.steps + 1, ptr(states), ptr(rewards), int(keep_all), ptr(self._stamp),
+                self._variant_code(), _lib.stream_ptr(dev)), 'glg_race_rollout')
+            self.steps += T
+            self._alive_known = None
+            return states, rewards
+
+    def _any_alive(self):
+        if self._alive_known is None:
+            self._stamp_host.copy_(self._stamp, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            self._alive_known = bool((self._stamp_host == self.steps).any())
+        return self._alive_known
+
+    def finished(self):
+        """games/race.py:502-504."""
+        return self.steps > self.steps_limit or not self._any_alive()
+
+    def winners(self):
+        """games/race.py:506-529 -> int64 [B] in {-1, 0..P-1}."""
+        B, P = self.num_tracks, self.num_players
+        out = torch.empty((B,), dtype=torch.int64, device=self.device)
+        check(_lib.lib().glg_race_winners(ptr(self.scores), ptr(self._finishes), ptr(self._valid_tracks), B, P,
+                                          self.steps_limit, ptr(out), _lib.stream_ptr(self.device)),
+              'glg_race_winners')
+        return out
+
+    def winner_stats(self, trials):
+        """Soft labels for the winner discriminator: one_hot(winners+1, P+1) averaged over `trials`
+        repetitions laid out trial-major (train-gan.py:84, 103-104) -> [B/trials, P+1] f32."""
+        w = self.winners()
+        boards = self.num_tracks // trials
+        out = torch.empty((boards, self.num_players + 1), dtype=torch.float32, device=self.device)
+        check(_lib.lib().glg_winner_stats(ptr(w), trials, boards, self.num_players, ptr(out),
+                                          _lib.stream_ptr(self.device)), 'glg_winner_stats')
+        return out
+
+    def iterate_valid(self, agents):
+        """games/race.py:336-338."""
+        valid = self._valid_tracks.tolist()
+        return ((i, a) for i, a in enumerate(agents) if valid[i])
+
+    # ---- reference attribute layouts (views / lazily materialised) ---------------------------------
+    alive = property(lambda self: None if self._alive is None else self._alive.view(torch.bool))
+    finishes = property(lambda self: None if self._finishes is None else self._finishes.view(torch.bool))
+
+    @property
+    def valid(self):
+        """bool [B*P], one entry per car (games/race.py:207)."""
+        if self._valid_tracks is None:
+            return None
+        return self._valid_tracks.view(torch.bool).view(-1, 1).repeat(1, self.num_players).view(-1)
+
+    right_vecs = property(lambda self: None if self._geom is None else self._geom[:, 0])
+    left_vecs = property(lambda self: None if self._geom is None else self._geom[:, 1])
+    segments = property(lambda self: None if self._geom is None else self._geom[:, 2])
+
+    def _lazy_get(self, name, fn):
+        if self._geom is None:
+            return None
+        if name not in self._lazy:
+            self._lazy[name] = fn()
+        return self._lazy[name]
+
+    @property
+    def right_bounds(self):     # games/race.py:166
+        return self._lazy_get('rb', lambda: torch.cat((self.right_vecs[:, :-1], self.right_vecs[:, 1:]), -1))
+
+    @property
+    def left_bounds(self):      # games/race.py:167
+        return self._lazy_get('lb', lambda: torch.cat((self.left_vecs[:, :-1], self.left_vecs[:, 1:]), -1))
+
+    def _per_player(self, x):
+        return x.unsqueeze(1).repeat(1, self.num_players, 1, 1).view(-1, *x.shape[-2:])
+
+    @property
+    def bounds(self):           # games/race.py:168-173, [B*P, 2L+3, 4]
+        def make():
+            start = torch.cat((self.left_vecs[:, :1], self.right_vecs[:, :1]), -1)
+            return self._per_player(torch.cat((self.right_bounds, self.left_bounds, start), 1))
+        return self._lazy_get('bounds', make)
+
+    @property
+    def reward_bound(self):     # games/race.py:169-171, [B*P, 1, 4]
+        return self._lazy_get('rwd', lambda: self._per_player(
+            torch.cat((self.left_vecs[:, -1:], self.right_vecs[:, -1:]), -1)))
+
+    @property
+    def line_bounds(self):      # games/race.py:175-177, [B*P, 2L+4, 2] on the host
+        return self._lazy_get('line', lambda: self._per_player(
+            torch.cat((self.right_vecs.flip(1), self.left_vecs), 1)).cpu())
+
+    @property
+    def history(self):
+        """[(positions, directions, actions, alive)] of board `record_id`, one entry per executed step
+        (games/race.py:492-494), materialised from the device-side ring on demand."""
+        if self._hist is None or not self._hist_steps:
+            return []
+        rows = self._hist[torch.tensor(self._hist_steps, device=self._hist.device)].cpu()
+        return [(r[:, 0:2].tolist(), r[:, 2:4].tolist(), [int(a) for a in r[:, 4].tolist()],
+                 [bool(a) for a in r[:, 5].tolist()]) for r in rows]

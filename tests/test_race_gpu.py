@@ -1,0 +1,185 @@
+"""Parity of the CUDA Race path (through the C ABI) against the reference-generated fixtures, the
+torch oracle and the C oracle.  These are the parity tests proper: run with `-m gpu` on a B200."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import RACE_CASES, eq, load_case, nmismatch, t
+
+pytestmark = pytest.mark.gpu
+
+QUANTISED = ['predef', 'iid9', 'loops', 'p1_crash', 'p4_short', 'agents']
+
+
+def make_env(case, variant, log_history=False):
+    from game_level_gan_b200.games import Race, RaceCar
+    cars = [RaceCar(*c) for c in case['cars'].tolist()]
+    return Race(timeout=float(case['timeout']), cars=cars, framerate=float(case['framerate']),
+                log_history=log_history, variant=variant)
+
+
+def replay(case, env, geometry=None, exact=True):
+    """Teacher-forced replay of a fixture; returns the number of mismatching elements per field."""
+    states, any_valid = env.reset(t(case['tracks']), geometry=geometry)
+    bad = dict(states=0, rewards=0, pos=0, dir=0, speed=0, alive=0, finishes=0, scores=0, finished=0, width=0)
+    assert any_valid == bool(case['any_valid'])
+    bad['states'] += nmismatch(states, case['states'][0])
+    bad['finished'] += int(env.finished() != bool(case['finished'][0]))
+    for s in range(case['actions'].shape[0]):
+        states, rewards = env.step(t(case['actions'][s]).cuda())
+        w = int(case['widths'][s + 1])
+        if states.size(-1) != w:
+            bad['width'] += 1
+            continue
+        bad['states'] += nmismatch(states, case['states'][s + 1][:, :, :w])
+        bad['rewards'] += nmismatch(rewards, case['rewards'][s])
+        for k, v in (('pos', env.positions), ('dir', env.directions), ('speed', env.speeds),
+                     ('alive', env.alive), ('finishes', env.finishes), ('scores', env.scores)):
+            bad[k] += nmismatch(v, case[k][s + 1])
+        bad['finished'] += int(env.finished() != bool(case['finished'][s + 1]))
+    return bad
+
+
+@pytest.mark.parametrize('variant', ['fast', 'brute'])
+@pytest.mark.parametrize('name', QUANTISED)
+def test_fixture_bit_exact_end_to_end(name, variant):
+    """Generator-like tracks (arcs in 1/4 steps): geometry, every step output and the winners are
+    bit-identical to the reference, building the geometry with our own kernel."""
+    c = load_case(name)
+    env = make_env(c, variant)
+    bad = replay(c, env)
+    assert eq(env.segments, c['centre']) and eq(env.left_vecs, c['left']) and eq(env.right_vecs, c['right'])
+    assert eq(env.valid, c['valid'])
+    assert all(v == 0 for v in bad.values()), bad
+    assert eq(env.winners(), c['winners'])
+
+
+@pytest.mark.parametrize('variant', ['fast', 'brute'])
+def test_fixture_float_tracks(variant):
+    """Arbitrary float arcs/widths: step parity is bit-exact on the reference's geometry; the build
+    itself differs from the reference's SLEEF sin/cos by a few ulp (tolerance 2e-5 absolute)."""
+    c = load_case('floatw')
+    env = make_env(c, variant)
+    bad = replay(c, env, geometry=(t(c['centre']), t(c['left']), t(c['right'])))
+    assert all(v == 0 for v in bad.values()), bad
+    assert eq(env.winners(), c['winners'])
+    env2 = make_env(c, variant)
+    env2.reset(t(c['tracks']))
+    for k, v in (('centre', env2.segments), ('left', env2.left_vecs), ('right', env2.right_vecs)):
+        np.testing.assert_allclose(v.cpu().numpy(), c[k], rtol=0, atol=2e-5)
+    assert eq(env2.valid, c['valid'])
+
+
+def test_attribute_layouts_and_history():
+    """Public attributes in the reference's layouts (games/race.py:161-190) and the history list."""
+    c = load_case('predef')
+    env = make_env(c, 'fast', log_history=True)
+    env.reset(t(c['tracks']))
+    B, P, N = 12, 2, 130
+    assert env.bounds.shape == (B * P, 2 * 129 + 1, 4) and env.reward_bound.shape == (B * P, 1, 4)
+    assert env.line_bounds.shape == (B * P, 2 * N, 2) and env.line_bounds.device.type == 'cpu'
+    assert env.left_bounds.shape == (B, 129, 4) and env.right_bounds.shape == (B, 129, 4)
+    assert env.positions.shape == (B, P, 2) and env.alive.dtype == torch.bool and env.scores.dtype == torch.int32
+    assert env.valid.shape == (B * P,) and env.valid.dtype == torch.bool
+    assert env.state_shape() == (20,) and env.actions == 9 and env.num_players == 2
+    from oracle import race_oracle as ro
+    walls, finish = ro.wall_table(t(c['left']), t(c['right']))
+    assert eq(env.bounds.view(B, P, -1, 4)[:, 1], walls) and eq(env.reward_bound.view(B, P, 1, 4)[:, 0], finish)
+    for s in range(5):
+        env.step(t(c['actions'][s]).cuda())
+    h = env.history
+    assert len(h) == 6                                   # reset's noop step + 5
+    pos, dirs, acts, alive = h[-1]
+    assert eq(torch.tensor(pos), c['pos'][5][0]) and eq(torch.tensor(dirs), c['dir'][5][0])
+    assert alive == c['alive'][5][0].tolist()
+    assert list(env.iterate_valid(['a'] * B)) == [(i, 'a') for i in range(B)]
+
+
+def _c_oracle_for(env, case_cars, framerate, timeout):
+    from oracle import c_oracle
+    from game_level_gan_b200.games import _tables
+    from oracle import race_oracle as ro
+    pr = _tables.race_params([ro.Car(*c) for c in case_cars], framerate, timeout, 18, 10.)
+    out = c_oracle.RaceParams()
+    ctypes.memmove(ctypes.byref(out), ctypes.byref(pr), ctypes.sizeof(out))
+    return c_oracle.CRace(out)
+
+
+@pytest.mark.parametrize('P', [2, 4])
+def test_free_running_rollout_vs_c_oracle(P):
+    """100-step free-running rollout on 512 iid-9 tracks, random + forward-biased actions: CUDA (fast and
+    brute) against the C oracle, every step, every output - bit-exact."""
+    from game_level_gan_b200.games import Race, RaceCar, _tables
+    cars = [(60., 4., 40.), (60., 1., 80.), (80., 2., 60.), (50., 3., 50.)][:P]
+    g = torch.Generator().manual_seed(99)
+    B, T = 512, 100
+    space = torch.linspace(-1., 1., 9)
+    tracks = torch.zeros(B, 128, 2)
+    tracks[:, :, 0] = space[torch.randint(0, 9, (B, 128), generator=g)]
+    acts = torch.randint(0, 9, (T, P, B), generator=g)
+    acts = torch.where(torch.rand((T, P, B), generator=g) < 0.5, torch.ones_like(acts), acts)
+    envs = {v: Race(timeout=40., cars=[RaceCar(*c) for c in cars], framerate=1. / 20., log_history=False,
+                    variant=v) for v in ('fast', 'brute')}
+    orc = _c_oracle_for(None, cars, 1. / 20., 40.)
+    st, ct, _ = _tables.heading_tables(128)
+    so, _ = orc.reset(tracks.numpy(), st.numpy(), ct.numpy())
+    bad = {v: 0 for v in envs}
+    for v, env in envs.items():
+        s0, _ = env.reset(tracks)
+        assert eq(env._geom.cpu().numpy(), orc.geom), 'geometry'
+        assert eq(env._valid_tracks, orc.valid)
+        bad[v] += nmismatch(s0, so)
+    for s in range(T):
+        so, ro_ = orc.step(acts[s].numpy())
+        for v, env in envs.items():
+            sg, rg = env.step(acts[s].cuda())
+            bad[v] += nmismatch(sg, so) + nmismatch(rg, ro_)
+            bad[v] += nmismatch(env.positions, orc.pos) + nmismatch(env.speeds, orc.speed)
+            bad[v] += nmismatch(env._alive, orc.alive) + nmismatch(env.scores, orc.scores)
+    assert bad == {'fast': 0, 'brute': 0}, bad
+    for env in envs.values():
+        assert eq(env.winners(), orc.winners())
+    assert int(orc.alive.sum()) < B * P            # the rollout really killed cars
+
+
+def test_rollout_equals_steps_and_winner_stats():
+    from game_level_gan_b200.games import Race, RaceConfig
+    g = torch.Generator().manual_seed(5)
+    trials, boards, T = 3, 40, 60
+    space = torch.linspace(-1., 1., 9)
+    base = torch.zeros(boards, 128, 2)
+    base[:, :, 0] = space[torch.randint(0, 9, (boards, 128), generator=g)]
+    tracks = base.repeat(trials, 1, 1)                  # trial-major, train-gan.py:84
+    B = trials * boards
+    acts = torch.randint(0, 9, (T, 2, B), generator=g)
+    a = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
+    b = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
+    a.reset(tracks)
+    b.reset(tracks)
+    per_step = [a.step(acts[s].cuda()) for s in range(T)]
+    states, rewards = b.rollout(acts.cuda(), keep_all=True)
+    assert eq(states, torch.stack([s for s, _ in per_step])) and eq(rewards, torch.stack([r for _, r in per_step]))
+    assert eq(a.positions, b.positions) and eq(a.scores, b.scores) and a.steps == b.steps
+    assert a.finished() == b.finished()
+    w = a.winners()
+    ref = torch.nn.functional.one_hot(w.cpu() + 1, 3).view(trials, -1, 3).float().mean(0)
+    assert eq(a.winner_stats(trials), ref)
+
+
+def test_empty_batch_and_errors():
+    from game_level_gan_b200.games import Race, RaceConfig
+    from game_level_gan_b200._lib import GlgError
+    env = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20.)
+    states, any_valid = env.reset(torch.zeros(0, 128, 2))
+    assert states.shape == (2, 0, 19) and any_valid is False and env.finished()
+    assert env.winners().shape == (0,)
+    env.reset(torch.zeros(3, 128, 2))
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(2, 4, dtype=torch.int64))
+    with pytest.raises(GlgError):
+        env.reset(torch.zeros(2, 600, 2))               # L beyond the kernel limit
+    with pytest.raises(GlgError):
+        Race(timeout=40., cars=RaceConfig.cars, device='cpu')
