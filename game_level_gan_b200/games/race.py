@@ -184,8 +184,9 @@ class Race(MultiEnvironment):
             actions = actions.detach().to(device=dev, dtype=torch.int64).contiguous()
             if tuple(actions.shape) != (P, B):
                 raise ValueError('actions must have shape [num_players, num_boards] = [%d, %d]' % (P, B))
+            anybody_alive = self._any_alive()              # state after the previous step
             self.steps += 1
-            if not self._any_alive():                      # games/race.py:353-356 (19-wide quirk)
+            if not anybody_alive:                          # games/race.py:353-356 (19-wide quirk)
                 states = torch.zeros((P, B, O + 1), dtype=torch.float32, device=dev)
                 rewards = (1. - self.finishes.float()) * self.negative_reward
                 return states, rewards.t()
