@@ -178,15 +178,10 @@ class Replica(object):
         self.env.reset(synthetic_tracks(B_TRACKS, seed))
         self.acts = synthetic_actions(PREROLL + CYCLE, P_CARS, B_TRACKS, seed + 1).to(device)
         self.env.rollout(self.acts[:PREROLL])
-        e = self.env
-        self.live = (e.positions, e.directions, e.speeds, e._alive, e._finishes, e.scores)
-        self.snap = tuple(x.clone() for x in self.live)
-        self.snap_steps = e.steps
+        self.snap = self.env.snapshot()
 
     def restore(self):
-        for dst, src in zip(self.live, self.snap):
-            dst.copy_(src, non_blocking=True)
-        self.env.steps = self.snap_steps
+        self.env.restore(self.snap)
 
     def cycle(self, n):
         self.restore()
@@ -212,7 +207,7 @@ def run_b200(args, rank, world):
         torch.cuda.synchronize()
 
     reps = [Replica(i, rank, device, args.variant) for i in range(REPLICAS)]
-    alive_start = float(torch.stack([r.snap[3].float().mean() for r in reps]).mean())
+    alive_start = float(torch.stack([r.snap['tensors'][3].float().mean() for r in reps]).mean())
 
     def run_steps(k):
         done, i = 0, 0
@@ -256,17 +251,14 @@ def run_b200(args, rank, world):
     host_acts = synthetic_actions(PREROLL + CYCLE, P_CARS, B_TRACKS, SEED + 78 + rank).pin_memory()
     for s in range(PREROLL):
         env.step(host_acts[s].to(device, non_blocking=True))
-    snap = tuple(x.clone() for x in (env.positions, env.directions, env.speeds, env._alive, env._finishes, env.scores))
-    live = (env.positions, env.directions, env.speeds, env._alive, env._finishes, env.scores)
+    snap = env.snapshot()
     out_s = torch.empty((P_CARS, B_TRACKS, O_RAYS + 2), dtype=torch.float32).pin_memory()
     out_r = torch.empty((P_CARS, B_TRACKS), dtype=torch.float32).pin_memory()
 
     def e2e_loop(k):
         for s in range(k):
             if s % CYCLE == 0:
-                for d_, s_ in zip(live, snap):
-                    d_.copy_(s_, non_blocking=True)
-                env.steps = PREROLL + 1
+                env.restore(snap)
             a = host_acts[PREROLL + s % CYCLE].to(device, non_blocking=True)      # H2D from pinned memory
             st, rw = env.step(a)
             out_s.copy_(st, non_blocking=True)                                    # D2H observations

@@ -63,7 +63,7 @@ SYMBOLS = {
     'glg_game_validate_tracks': (ctypes.c_int, [_vp, _vp, _vp]),
     'glg_game_update_players': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     'glg_game_smallest_distance': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
-    'glg_pacman_step': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    'glg_pacman_step': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     'glg_pacman_observe': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
 }
 

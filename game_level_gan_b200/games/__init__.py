@@ -1,6 +1,10 @@
 """`games` package of the reference, B200-native (games/__init__.py:1-4)."""
 from .environment import MultiEnvironment
+from .pacman import Pacman
 from .race import Race, RaceCar
 from .race_utils import RaceConfig, predefined_tracks, race_game
+from .pytorch_wrapper import PytorchWrapper
+from . import game_helpers
 
-__all__ = ['MultiEnvironment', 'Race', 'RaceCar', 'RaceConfig', 'predefined_tracks', 'race_game']
+__all__ = ['MultiEnvironment', 'Pacman', 'Race', 'RaceCar', 'RaceConfig', 'predefined_tracks', 'race_game',
+           'PytorchWrapper', 'game_helpers']

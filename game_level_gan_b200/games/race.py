@@ -228,6 +228,21 @@ class Race(MultiEnvironment):
             self._alive_known = None
             return states, rewards
 
+    def snapshot(self):
+        """Copy of the mutable episode state (the reference has no env checkpoint; used to rewind
+        rollouts, e.g. by bench.py).  Geometry and validity are not part of it."""
+        live = (self.positions, self.directions, self.speeds, self._alive, self._finishes, self.scores)
+        return {'tensors': tuple(x.clone() for x in live), 'steps': self.steps,
+                'alive_known': self._any_alive()}
+
+    def restore(self, snap):
+        """Rewind to a `snapshot()` of the same episode (device copies only, no host sync)."""
+        live = (self.positions, self.directions, self.speeds, self._alive, self._finishes, self.scores)
+        for dst, src in zip(live, snap['tensors']):
+            dst.copy_(src, non_blocking=True)
+        self.steps = snap['steps']
+        self._alive_known = snap['alive_known']
+
     def _any_alive(self):
         if self._alive_known is None:
             self._stamp_host.copy_(self._stamp, non_blocking=True)

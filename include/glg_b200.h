@@ -187,9 +187,10 @@ int glg_game_smallest_distance(glg_game* game, const int64_t* idx, const float* 
  *   grid    [B,H,W,4+P] i32 (the 4+P "real" channels of the reference's [B,H,W,4+2P] grid)
  *   players [B*P,4] i32 rows (b,x,y,p) in the reference's np.where order (pacman.py:59-61)
  *   actions [B,P] i32 (0..4), rewards [P,B] f64 out (the reference returns float64 rewards)
+ *   scratch [1] i32 device word (the batch-wide "somebody can move" flag of pacman.py:77)
  * ------------------------------------------------------------------------------------------ */
 int glg_pacman_step(int32_t* grid, int32_t* players, const int32_t* actions, double* rewards,
-                    int32_t B, int32_t H, int32_t W, int32_t P, glg_stream_t stream);
+                    int32_t* scratch, int32_t B, int32_t H, int32_t W, int32_t P, glg_stream_t stream);
 /* obs [P,B,H,W,4+2P] f32 out: grid channels, zeros, and 1.0 in channel 4+P+p (pacman.py:107-109) */
 int glg_pacman_observe(const int32_t* grid, float* obs, int32_t B, int32_t H, int32_t W, int32_t P,
                        glg_stream_t stream);

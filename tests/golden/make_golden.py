@@ -222,5 +222,73 @@ def main():
                         out=R._rotate_vecs(v, a).numpy(), car_angle=ang.numpy())
 
 
+def import_reference_pacman():
+    """games/pacman.py indexes with lists of arrays (`grid[list(idx.T)]`), which numpy >= 1.23 rejects
+    (SURVEY.md section 2, row 5).  The only change made here is list(...) -> tuple(...) at those five
+    places; the source is patched in memory, nothing is written to disk."""
+    import types
+    src = open(os.path.join(REF, 'games', 'pacman.py')).read()
+    src = src.replace('from .environment import MultiEnvironment', 'MultiEnvironment = object')
+    for a, b in (('self.grid[list(pos_ins.T)]', 'self.grid[tuple(pos_ins.T)]'),
+                 ('positions = list(np.transpose(self.players + np.array([0, 0, 0, self.fields])))',
+                  'positions = tuple(np.transpose(self.players + np.array([0, 0, 0, self.fields])))'),
+                 ('small = list(small.T)', 'small = tuple(small.T)'),
+                 ('large = list(large.T)', 'large = tuple(large.T)')):
+        assert a in src
+        src = src.replace(a, b)
+    mod = types.ModuleType('ref_pacman')
+    exec(compile(src, 'ref_pacman.py', 'exec'), mod.__dict__)
+    return mod.Pacman
+
+
+def random_levels(B, H, W, P, rng, corners=True):
+    """Levels like generators/pacman_generator.py:56-63: iid fields, players in the corners."""
+    fields = rng.choice(4, size=(B, H, W), p=[0.4, 0.5, 0.07, 0.03])
+    board = np.zeros((B, H, W, 4 + P), dtype=np.int32)
+    np.put_along_axis(board[..., :4], fields[..., None], 1, axis=-1)
+    spots = [(0, 0), (H - 1, W - 1), (0, W - 1), (H - 1, 0)]
+    for b in range(B):
+        for p in range(P):
+            x, y = spots[p] if corners else (rng.integers(0, H), rng.integers(0, W))
+            board[b, x, y, :4] = 0
+            board[b, x, y, 0] = 1          # players start on an empty cell
+            board[b, x, y, 4 + p] = 1
+    return board
+
+
+def run_pacman_case(Pacman, name, board, P, T, rng, actions=None):
+    B, H, W = board.shape[:3]
+    env = Pacman((H, W), P, batch_size=B)
+    obs = env.reset(board.copy())
+    grids, rewards, acts = [env.grid.copy()], [], []
+    first_obs = np.stack(obs)
+    for t in range(T):
+        a = actions[t] if actions is not None else rng.integers(0, 5, size=(B, P)).astype(np.int32)
+        acts.append(a)
+        obs, rew = env.step(a)
+        grids.append(env.grid.copy())
+        rewards.append(np.stack(rew))
+    np.savez_compressed(os.path.join(HERE, 'pacman_%s.npz' % name), board=board, actions=np.stack(acts),
+                        grids=np.stack(grids).astype(np.int8), rewards=np.stack(rewards),
+                        first_obs=first_obs, last_obs=np.stack(obs), players=env.players)
+    print('pacman_%-10s B=%d %dx%d P=%d T=%d reward_sum=%.2f' % (name, B, H, W, P, T, float(np.sum(rewards))))
+
+
+def main_pacman():
+    Pacman = import_reference_pacman()
+    rng = np.random.default_rng(20261018)
+    run_pacman_case(Pacman, 'p2', random_levels(6, 15, 15, 2, rng), 2, 40, rng)
+    run_pacman_case(Pacman, 'p3', random_levels(4, 9, 11, 3, rng), 3, 30, rng)          # np.where order quirk
+    run_pacman_case(Pacman, 'p4_random', random_levels(3, 7, 7, 4, rng, corners=False), 4, 30, rng)
+    # single board where nobody can move on some steps (batch-wide skip, pacman.py:77)
+    board, size, P = Pacman.from_str('#####\n#1s2#\n#####')
+    acts = np.array([[[1, 1]], [[2, 2]], [[4, 3]], [[1, 2]], [[3, 4]], [[0, 0]]], dtype=np.int32)
+    run_pacman_case(Pacman, 'walled', board, P, len(acts), rng, actions=acts)
+
+
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'pacman':
+        main_pacman()
+    else:
+        main()
+        main_pacman()
