@@ -24,10 +24,15 @@ constexpr float INF = __builtin_huge_valf();
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
-// points of one track record {right[N], left[N], centre[N]} (include/glg_b200.h)
+// One track record in HBM / shared memory (include/glg_b200.h): 3*N float2,
+//   line[0..N)   = right boundary REVERSED (line[v] = right[N-1-v])
+//   line[N..2N)  = left boundary
+//   centre[0..N) = centre points
+// so that `line` is the polyline right-end ... start line ... left-end (the reference's own
+// line_bounds order, games/race.py:175) and wall w of the polyline joins line[w] and line[w+1]:
+// w < N-1 right walls, w == N-1 the start line, w >= N left walls (2N-1 walls).
 struct TrackView {
-    const float2* right;
-    const float2* left;
+    const float2* line;
     const float2* centre;
     int N;
 };

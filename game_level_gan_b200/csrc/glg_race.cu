@@ -7,7 +7,7 @@
 //   glg_winner_stats  train-gan.py:103-104    one_hot(winners+1).view(trials,-1,P+1).mean(0)
 //
 // Mapping: one CTA per track, one warp per car.  The CTA stages the track record
-// {right, left, centre} (3*N float2, 3120 B at L=128) in shared memory once; each warp then runs
+// {line, centre} (3*N float2, 3120 B at L=128) in shared memory with one bulk async copy (TMA); each warp then runs
 // kinematics, progress arg-min, wall/finish collision, reward/score, and the ray-cast sensors for
 // its car with the lanes striding over points / walls, and packs the [P,B,O+2] observation.
 // There is no cross-car dependence in the reference step, so no global sync.
@@ -46,28 +46,55 @@ __global__ void race_init_kernel(glg_race_state st, int K, int32_t* alive_stamp)
     st.scores[k] = 0;
 }
 
-template <int VARIANT>
-__global__ void __launch_bounds__(32 * GLG_MAX_PLAYERS)
+// ---- bulk async copy (TMA, 1-D) of one track record into shared memory ---------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void record_copy_async(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    const uint32_t b = smem_u32(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+
+__device__ __forceinline__ void record_copy_wait(uint64_t* bar) {
+    const uint32_t b = smem_u32(bar);
+    uint32_t done = 0;
+    for (int spin = 0; !done; ++spin) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(b) : "memory");
+        if (spin > (1 << 22)) __trap();          // never hang the device on a lost copy
+    }
+}
+
+// OC: number of rays known at compile time (0 = generic)
+template <int VARIANT, int OC>
+__global__ void __launch_bounds__(32 * GLG_MAX_PLAYERS, 4)
 race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int N = a.N, B = a.B;
-    const int P = pr.num_players, O = pr.num_rays;
+    const int P = pr.num_players;
+    const int O = OC ? OC : pr.num_rays;
     const int b = blockIdx.x;
     const int lane = lane_id();
     const int p = threadIdx.x >> 5;
 
-    // ---- stage the track record (coalesced 8-byte loads; the record is contiguous in HBM) ----
+    // ---- stage the track record {line[2N], centre[N]} (contiguous, 24N bytes) in shared memory ----
     float2* pts = reinterpret_cast<float2*>(smem_raw);
-    {
-        const float2* rec = reinterpret_cast<const float2*>(a.geom) + (size_t)b * 3 * N;
+    const float2* rec = reinterpret_cast<const float2*>(a.geom) + (size_t)b * 3 * N;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + smem_barrier_offset(N));
+    const uint32_t rec_bytes = (uint32_t)(3 * N * sizeof(float2));
+    // one elected thread issues a single bulk copy when the record is 16-byte granular (N even)
+    const bool bulk = VARIANT == GLG_STEP_FAST && (rec_bytes & 15u) == 0 && ((uintptr_t)a.geom & 15u) == 0;
+    if (bulk) {
+        if (threadIdx.x == 0) record_copy_async(pts, rec, rec_bytes, bar);
+    } else {
         for (int i = threadIdx.x; i < 3 * N; i += blockDim.x) pts[i] = __ldg(&rec[i]);
     }
-    __syncthreads();
-    TrackView tv{pts, pts + N, pts + 2 * N, N};
-    SensorScratch* scratch = reinterpret_cast<SensorScratch*>(smem_raw + sensor_scratch_offset(N)) + p;
 
-    // ---- car state (uniform across the warp) ----
+    // ---- car state and kinematics while the copy is in flight (uniform across the warp) ----
     const int k = b * P + p;
     bool alive = a.st.alive[k] != 0;
     bool fin = a.st.finishes[k] != 0;
@@ -76,7 +103,6 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
     act = min(max(act, 0), 8);
     if (!alive || !ok) act = 0;                                           // race.py:359
     const int fs = c_steer_idx[act], ft = c_throttle_idx[act];
-
     const float2 dir = reinterpret_cast<const float2*>(a.st.directions)[k];
     const float2 pos = reinterpret_cast<const float2*>(a.st.positions)[k];
     const float c = pr.turn_cos[p][fs], s = pr.turn_sin[p][fs];
@@ -88,37 +114,56 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
     const P2 op{pos.x, pos.y};
     const P2 np{xadd(pos.x, xmul(nd.x, nv)), xadd(pos.y, xmul(nd.y, nv))}; // race.py:372
 
-    // ---- progress: first arg-min of the distance to the centre points (race.py:374-376) ----
-    int idx = 0;
+    __syncthreads();                     // barrier init / plain loads visible to every warp
+    if (bulk) record_copy_wait(bar);
+    const TrackView tv{pts, pts + 2 * N, N};
+    SensorScratch* scratch = reinterpret_cast<SensorScratch*>(smem_raw + smem_scratch_offset(N)) + p;
+
+    // ---- progress: FIRST arg-min of |np - centre_j| (race.py:374-376) ----
+    // norm = sqrt_rn(q), q = fma(ey,ey,ex*ex); sqrt is monotone, so the winner is the first j whose
+    // sqrt_rn(q_j) equals sqrt_rn(min q): only values within a few ulp of the minimum need the sqrt.
+    int idx;
     {
-        float best = INF;
+        float qmin = INF;
         for (int j = lane; j < N; j += 32) {
             const float2 cpt = tv.centre[j];
-            const float d = norm2(xsub(np.x, cpt.x), xsub(np.y, cpt.y));
-            if (d < best) { best = d; idx = j; }
+            const float ex = xsub(np.x, cpt.x), ey = xsub(np.y, cpt.y);
+            qmin = fminf(qmin, __fmaf_rn(ey, ey, xmul(ex, ex)));
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const float od = __shfl_xor_sync(FULL, best, off);
-            const int oj = __shfl_xor_sync(FULL, idx, off);
-            if (od < best || (od == best && oj < idx)) { best = od; idx = oj; }
+        qmin = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(qmin)));        // q >= 0
+        const float smin = __fsqrt_rn(qmin);
+        const float qcut = qmin * 1.000001f + 1e-45f;
+        int first = 0x7fffffff;
+        for (int j = lane; j < N; j += 32) {
+            const float2 cpt = tv.centre[j];
+            const float ex = xsub(np.x, cpt.x), ey = xsub(np.y, cpt.y);
+            const float q = __fmaf_rn(ey, ey, xmul(ex, ex));
+            if (q <= qcut && first == 0x7fffffff && __fsqrt_rn(q) == smin) first = j;
         }
+        idx = (int)__reduce_min_sync(FULL, (unsigned)first);
     }
 
-    // ---- collisions with the walls and the finish line (race.py:380-447) ----
+    // ---- collisions (race.py:380-447) and sensor candidates in one pass over the polyline ----
     float reward = fin ? 0.f : pr.step_penalty;                            // race.py:382-383
     const bool upd = alive && moving && ok;                                // race.py:380
+    ScanResult scan{false, true, 0};
+    if (VARIANT == GLG_STEP_FAST) {
+        if (alive) scan = scan_fast<OC>(tv, pr, np, nd, op, upd, scratch);
+    } else if (upd) {
+        scan.wall_hit = collide_brute(tv, op, np);
+    }
     if (upd) {
-        const int S = N - 1;
-        bool hit = false;
-        for (int j = lane; j < 2 * S + 1; j += 32) {                       // race.py:406-407
-            P2 wp, wq;
-            wall_points(tv, j, wp, wq);
-            hit = hit || segments_cross(wp, wq, op, np);
+        const bool dead = scan.wall_hit;
+        const float2 fl = tv.line[2 * N - 1], fr = tv.line[0];             // finish: left[N-1] -> right[N-1], race.py:169
+        bool done = false;
+        {   // box test first: the finish line is far away on almost every step
+            const float x0 = fminf(op.x, np.x) - BOX_MARGIN, x1 = fmaxf(op.x, np.x) + BOX_MARGIN;
+            const float y0 = fminf(op.y, np.y) - BOX_MARGIN, y1 = fmaxf(op.y, np.y) + BOX_MARGIN;
+            const bool apart = fmaxf(fl.x, fr.x) < x0 || fminf(fl.x, fr.x) > x1 ||
+                               fmaxf(fl.y, fr.y) < y0 || fminf(fl.y, fr.y) > y1;
+            if (VARIANT == GLG_STEP_BRUTE || !apart)
+                done = segments_cross(P2{fl.x, fl.y}, P2{fr.x, fr.y}, op, np);   // race.py:431-432
         }
-        const bool dead = __any_sync(FULL, hit);
-        const float2 fl = tv.left[N - 1], fr = tv.right[N - 1];            // race.py:169, 431-432
-        const bool done = segments_cross(P2{fl.x, fl.y}, P2{fr.x, fr.y}, op, np);
         reward = xadd(reward, xsub(done ? 1.f : 0.f, dead ? 1.f : 0.f));   // race.py:434
         alive = alive && !dead && !done;                                   // race.py:414, 435
         fin = fin || done;                                                 // race.py:436
@@ -146,23 +191,23 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
         }
     }
 
-    // ---- sensors (race.py:459-489): lane i ends up holding the reading of ray i ----
-    float obs = 0.f;
+    // ---- sensors (race.py:459-489) and observation pack [P,B,O+2] (race.py:496-500) ----
+    // lane i < O: clamp(t_i, max)/max; lane O: speed/vmax (:497); lane O+1: idx/3 (:376) - one division
+    float num = 0.f, den = 1.f;
     if (alive) {
-        float t;
-        if (VARIANT == GLG_STEP_BRUTE) t = sensors_brute(tv, pr, np, nd, scratch);
-        else t = sensors_fast(tv, pr, np, nd, scratch);
-        // clamp(max)/max_distance (race.py:489); NaN propagates like torch.clamp
-        obs = (t != t) ? t : xdiv(fminf(t, pr.max_distance), pr.max_distance);
+        const float t = (VARIANT == GLG_STEP_FAST) ? sensors_finish(tv, pr, np, nd, scratch, scan, O)
+                                                   : sensors_brute(tv, pr, np, nd);
+        num = (t != t) ? t : fminf(t, pr.max_distance);                    // NaN propagates like torch.clamp
+        den = pr.max_distance;
     }
-    // ---- observation pack [P,B,O+2] (race.py:496-500) ----
     float* out = a.states_out + ((size_t)p * B + b) * (O + 2);
-    if (lane < O) out[lane] = obs;
-    else if (lane == O) out[O] = xdiv(speed, pr.vmax[p]);                  // race.py:497
-    else if (lane == O + 1) out[O + 1] = xdiv((float)idx, pr.progress_div);   // race.py:376
+    if (lane == O) { num = speed; den = pr.vmax[p]; }
+    if (lane == O + 1) { num = (float)idx; den = pr.progress_div; }
+    const float val = xdiv(num, den);
+    if (lane < O + 2) out[lane] = val;
     if (O + 2 > 32 && lane == 0) {                                         // O in {31, 32}
-        if (O == 31) out[O + 1] = xdiv((float)idx, pr.progress_div);
-        else { out[O] = xdiv(speed, pr.vmax[p]); out[O + 1] = xdiv((float)idx, pr.progress_div); }
+        if (O == 32) out[O] = xdiv(speed, pr.vmax[p]);
+        out[O + 1] = xdiv((float)idx, pr.progress_div);
     }
 }
 
@@ -213,11 +258,13 @@ static int launch_step(const glg_race_params* pr, const StepArgs& a, int variant
 {
     const int P = pr->num_players;
     if (variant == GLG_STEP_FAST && (pr->num_rays & 1)) variant = GLG_STEP_BRUTE;   // pruning pairs opposite rays
-    const size_t smem = sensor_scratch_offset(a.N) + (size_t)P * sizeof(SensorScratch);
+    const size_t smem = smem_scratch_offset(a.N) + (size_t)P * sizeof(SensorScratch);
     if (variant == GLG_STEP_BRUTE)
-        race_step_kernel<GLG_STEP_BRUTE><<<a.B, 32 * P, smem, stream>>>(*pr, a);
+        race_step_kernel<GLG_STEP_BRUTE, 0><<<a.B, 32 * P, smem, stream>>>(*pr, a);
+    else if (pr->num_rays == 18)
+        race_step_kernel<GLG_STEP_FAST, 18><<<a.B, 32 * P, smem, stream>>>(*pr, a);
     else
-        race_step_kernel<GLG_STEP_FAST><<<a.B, 32 * P, smem, stream>>>(*pr, a);
+        race_step_kernel<GLG_STEP_FAST, 0><<<a.B, 32 * P, smem, stream>>>(*pr, a);
     return GLG_OK;
 }
 

@@ -3,8 +3,8 @@
 //   glg_track_build    replaces games/race.py:126-158  (Race.reset, geometry part)
 //   glg_track_validate replaces games/race.py:326-334  (Race._is_correct) as used at :199-200
 //
-// HBM layout of the result: one record {right[N], left[N], centre[N]} of float2 per track
-// (include/glg_b200.h).  Both kernels are "reset-time" work, amortised over hundreds of steps.
+// HBM layout of the result: one record {right[N] reversed, left[N], centre[N]} of float2 per track
+// (include/glg_b200.h, glg_common.cuh TrackView).  Both kernels are "reset-time" work, amortised over hundreds of steps.
 #include <math.h>
 
 #include "glg_common.cuh"
@@ -91,7 +91,7 @@ track_build_kernel(const float* __restrict__ tracks, int B, int L,
             oy = xmul(xdiv(ny, len), w);
         }
         const float2 c = cen[j];
-        rec[j] = make_float2(xadd(c.x, ox), xadd(c.y, oy));              // right
+        rec[N - 1 - j] = make_float2(xadd(c.x, ox), xadd(c.y, oy));      // right, stored reversed
         rec[N + j] = make_float2(xadd(c.x, -ox), xadd(c.y, -oy));        // left
         rec[2 * N + j] = c;                                              // centre
     }
@@ -112,10 +112,10 @@ __global__ void track_validate_kernel(const float* __restrict__ geom, int B, int
     if (threadIdx.x == 0) bad_flag = 0;
     for (int j = threadIdx.x; j < M; j += blockDim.x) {   // race.py:166-172 + finish line :169
         float2 p, q;
-        if (j < S) { p = rec[j]; q = rec[j + 1]; }
-        else if (j < 2 * S) { p = rec[N + j - S]; q = rec[N + j - S + 1]; }
-        else if (j == 2 * S) { p = rec[N]; q = rec[0]; }
-        else { p = rec[N + N - 1]; q = rec[N - 1]; }
+        if (j < S) { p = rec[N - 1 - j]; q = rec[N - 2 - j]; }              // right[j] -> right[j+1]
+        else if (j < 2 * S) { p = rec[N + j - S]; q = rec[N + j - S + 1]; }  // left[j-S] -> left[j-S+1]
+        else if (j == 2 * S) { p = rec[N]; q = rec[N - 1]; }                 // start: left[0] -> right[0]
+        else { p = rec[2 * N - 1]; q = rec[0]; }                             // finish: left[N-1] -> right[N-1]
         lines[j] = make_float4(p.x, p.y, q.x, q.y);
     }
     __syncthreads();
@@ -136,7 +136,7 @@ __global__ void track_validate_kernel(const float* __restrict__ geom, int B, int
             const int o1 = turn(ap, aq, cp), o2 = turn(ap, aq, cq);
             const int o3 = turn(cp, cq, ap), o4 = turn(cp, cq, aq);
             if (o1 * o2 < 0 && o3 * o4 < 0) bad_flag = 1;
-            if ((m & 63) == 63 && bad_flag) break;
+            if ((m & 63) == 63 && *(volatile int*)&bad_flag) break;
         }
     }
     __syncthreads();

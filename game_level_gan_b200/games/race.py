@@ -148,7 +148,7 @@ class Race(MultiEnvironment):
             self._geom = torch.empty((B, 3, N, 2), dtype=torch.float32, device=dev)
             if geometry is not None:
                 centre, left, right = (g.to(device=dev, dtype=torch.float32) for g in geometry)
-                self._geom[:, 0], self._geom[:, 1], self._geom[:, 2] = right, left, centre
+                self._geom[:, 0], self._geom[:, 1], self._geom[:, 2] = right.flip(1), left, centre
             else:
                 st, ct, half = self._heading_tables(L)
                 check(lib.glg_track_build(ptr(tracks), B, L, ptr(st), ptr(ct), half, ptr(self._geom), stream),
@@ -289,7 +289,8 @@ class Race(MultiEnvironment):
             return None
         return self._valid_tracks.view(torch.bool).view(-1, 1).repeat(1, self.num_players).view(-1)
 
-    right_vecs = property(lambda self: None if self._geom is None else self._geom[:, 0])
+    # the track record keeps the right boundary reversed (polyline order, csrc/glg_common.cuh)
+    right_vecs = property(lambda self: self._lazy_get('right', lambda: self._geom[:, 0].flip(1)))
     left_vecs = property(lambda self: None if self._geom is None else self._geom[:, 1])
     segments = property(lambda self: None if self._geom is None else self._geom[:, 2])
 

@@ -78,11 +78,13 @@ typedef struct glg_race_state {
 
 /* ------------------------------------------------------------------------------------------
  * Track geometry in HBM: one contiguous record per track,
- *     geom[b] = { right[N] , left[N] , centre[N] }  each point (x,y) f32,   N = L + 2,
- * i.e. a [B,3,N,2] f32 tensor (3*N*8 bytes per track = 3120 B at L = 128, 16-byte aligned so the
- * step kernel can stage a record with one bulk async copy).  Walls, start and finish lines are
- * derived from consecutive points on the fly; the reference's per-player duplicated
- * `bounds [B*P,2L+3,4]` (race.py:172-173) is never materialised on the hot path.
+ *     geom[b] = { right[N] REVERSED , left[N] , centre[N] }  each point (x,y) f32,   N = L + 2,
+ * i.e. a [B,3,N,2] f32 tensor whose first 2N points form the polyline right-end .. start line ..
+ * left-end (the order of the reference's own `line_bounds`, games/race.py:175), followed by the
+ * centre points.  3*N*8 bytes per track = 3120 B at L = 128, 16-byte granular, so the step kernel
+ * stages a record with ONE bulk async copy (TMA).  Walls, start and finish lines are consecutive
+ * point pairs; the reference's per-player duplicated `bounds [B*P,2L+3,4]` (race.py:172-173) is
+ * never materialised on the hot path.
  * ------------------------------------------------------------------------------------------ */
 
 /* Generator output -> geometry.  Replaces games/race.py:126-158 (Race.reset, geometry part).
