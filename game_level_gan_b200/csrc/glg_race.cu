@@ -118,14 +118,29 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
     if (bulk) record_copy_wait(bar);
     const TrackView tv{pts, pts + 2 * N, N};
     SensorScratch* scratch = reinterpret_cast<SensorScratch*>(smem_raw + smem_scratch_offset(N)) + p;
+    unsigned* maskbuf = reinterpret_cast<unsigned*>(smem_raw + smem_maskbuf_offset(N, P)) + (size_t)p * maskbuf_len(N);
 
     // ---- progress: FIRST arg-min of |np - centre_j| (race.py:374-376) ----
     // norm = sqrt_rn(q), q = fma(ey,ey,ex*ex); sqrt is monotone, so the winner is the first j whose
     // sqrt_rn(q_j) equals sqrt_rn(min q): only values within a few ulp of the minimum need the sqrt.
     int idx;
     {
+        constexpr int KEEP = 5;                   // N <= 160 (L <= 158): every q stays in a register
+        float qk[KEEP];
         float qmin = INF;
-        for (int j = lane; j < N; j += 32) {
+#pragma unroll
+        for (int u = 0; u < KEEP; ++u) {
+            const int j = lane + 32 * u;
+            float q = INF;
+            if (j < N) {
+                const float2 cpt = tv.centre[j];
+                const float ex = xsub(np.x, cpt.x), ey = xsub(np.y, cpt.y);
+                q = __fmaf_rn(ey, ey, xmul(ex, ex));
+            }
+            qk[u] = q;
+            qmin = fminf(qmin, q);
+        }
+        for (int j = lane + 32 * KEEP; j < N; j += 32) {
             const float2 cpt = tv.centre[j];
             const float ex = xsub(np.x, cpt.x), ey = xsub(np.y, cpt.y);
             qmin = fminf(qmin, __fmaf_rn(ey, ey, xmul(ex, ex)));
@@ -134,11 +149,16 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
         const float smin = __fsqrt_rn(qmin);
         const float qcut = qmin * 1.000001f + 1e-45f;
         int first = 0x7fffffff;
-        for (int j = lane; j < N; j += 32) {
-            const float2 cpt = tv.centre[j];
-            const float ex = xsub(np.x, cpt.x), ey = xsub(np.y, cpt.y);
-            const float q = __fmaf_rn(ey, ey, xmul(ex, ex));
-            if (q <= qcut && first == 0x7fffffff && __fsqrt_rn(q) == smin) first = j;
+#pragma unroll
+        for (int u = KEEP - 1; u >= 0; --u)
+            if (qk[u] <= qcut && __fsqrt_rn(qk[u]) == smin) first = lane + 32 * u;
+        if (first == 0x7fffffff) {
+            for (int j = lane + 32 * KEEP; j < N; j += 32) {
+                const float2 cpt = tv.centre[j];
+                const float ex = xsub(np.x, cpt.x), ey = xsub(np.y, cpt.y);
+                const float q = __fmaf_rn(ey, ey, xmul(ex, ex));
+                if (q <= qcut && __fsqrt_rn(q) == smin) { first = j; break; }
+            }
         }
         idx = (int)__reduce_min_sync(FULL, (unsigned)first);
     }
@@ -148,7 +168,7 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
     const bool upd = alive && moving && ok;                                // race.py:380
     ScanResult scan{false, true, 0};
     if (VARIANT == GLG_STEP_FAST) {
-        if (alive) scan = scan_fast<OC>(tv, pr, np, nd, op, upd, scratch);
+        if (alive) scan = scan_fast<OC>(tv, pr, np, nd, op, upd, scratch, maskbuf);
     } else if (upd) {
         scan.wall_hit = collide_brute(tv, op, np);
     }
@@ -258,7 +278,7 @@ static int launch_step(const glg_race_params* pr, const StepArgs& a, int variant
 {
     const int P = pr->num_players;
     if (variant == GLG_STEP_FAST && (pr->num_rays & 1)) variant = GLG_STEP_BRUTE;   // pruning pairs opposite rays
-    const size_t smem = smem_scratch_offset(a.N) + (size_t)P * sizeof(SensorScratch);
+    const size_t smem = smem_total(a.N, P);
     if (variant == GLG_STEP_BRUTE)
         race_step_kernel<GLG_STEP_BRUTE, 0><<<a.B, 32 * P, smem, stream>>>(*pr, a);
     else if (pr->num_rays == 18)

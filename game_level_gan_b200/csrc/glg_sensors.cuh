@@ -19,9 +19,9 @@
 
 namespace glg {
 
-constexpr int QUEUE_CAP = 160;   // (wall, ray) candidates buffered per warp before a dense evaluation
+constexpr int QUEUE_CAP = 192;   // (wall, ray) candidates evaluated per car before falling back to BRUTE
 
-struct SensorScratch {           // per-warp shared memory
+struct SensorScratch {           // per-warp shared memory (fixed part)
     float4 ray[GLG_MAX_RAYS];    // dx, dy, far x, far y per ray
     int tmin[GLG_MAX_RAYS];      // running min of t as ordered int bits (t >= 0, -0.0 or +inf)
     unsigned nan_mask;           // rays that saw a NaN
@@ -29,11 +29,19 @@ struct SensorScratch {           // per-warp shared memory
     unsigned short queue[QUEUE_CAP];
 };
 
-// shared memory carve-up of the step kernel: [record 3N float2][mbarrier 16 B][P x SensorScratch]
+// shared memory carve-up of the step kernel:
+//   [record 3N float2][mbarrier 16 B][P x SensorScratch][P x maskbuf(2N u32, padded to 32)]
 __host__ __device__ inline size_t smem_barrier_offset(int N) {
     return ((size_t)3 * N * sizeof(float2) + 15) & ~(size_t)15;
 }
 __host__ __device__ inline size_t smem_scratch_offset(int N) { return smem_barrier_offset(N) + 16; }
+__host__ __device__ inline int maskbuf_len(int N) { return ((2 * N + 31) / 31 + 1) * 32; }
+__host__ __device__ inline size_t smem_maskbuf_offset(int N, int P) {
+    return smem_scratch_offset(N) + (size_t)P * sizeof(SensorScratch);
+}
+__host__ __device__ inline size_t smem_total(int N, int P) {
+    return smem_maskbuf_offset(N, P) + (size_t)P * maskbuf_len(N) * sizeof(unsigned);
+}
 
 // wall w of the polyline in the reference's orientation (games/race.py:166-168): right walls and the
 // start line run against the polyline direction (right[j] -> right[j+1], left[0] -> right[0]).
@@ -157,13 +165,15 @@ __device__ __forceinline__ void queue_flush(const TrackView& tv, P2 s, SensorScr
 struct ScanResult {
     bool wall_hit;   // the path op -> s crosses a wall (valid if need_col)
     bool safe;       // preconditions of the pruning held; otherwise the caller must use sensors_brute
-    int queued;      // candidates still in the queue
+    int queued;      // candidates in the queue
 };
 
 // OC: compile-time number of rays (0 = take it from pr at run time)
+// maskbuf: per-warp u32[maskbuf_len(N)]; slot pass*32+lane holds the candidate-ray mask of the wall that
+// lane owned in that pass (written and later re-read by the same lane).
 template <int OC>
 __device__ __forceinline__ ScanResult scan_fast(const TrackView& tv, const glg_race_params& pr, P2 s, P2 nd, P2 op,
-                                                bool need_col, SensorScratch* sc)
+                                                bool need_col, SensorScratch* sc, unsigned* maskbuf)
 {
     const int lane = lane_id();
     const int O = OC ? OC : pr.num_rays;        // even (the host routes odd O to BRUTE)
@@ -179,7 +189,6 @@ __device__ __forceinline__ ScanResult scan_fast(const TrackView& tv, const glg_r
         sc->tmin[lane] = 0x7f800000;
     }
     if (lane == 0) sc->nan_mask = 0;
-    __syncwarp();
 
     const float sect = (float)O * (0.5f / PI_F);         // radians -> sector units
     const float m_eta = ETA_ANGLE * sect;
@@ -190,11 +199,12 @@ __device__ __forceinline__ ScanResult scan_fast(const TrackView& tv, const glg_r
     const float bx0 = need_col ? fminf(ox, 0.f) - BOX_MARGIN : INF, bx1 = need_col ? fmaxf(ox, 0.f) + BOX_MARGIN : -INF;
     const float by0 = fminf(oy, 0.f) - BOX_MARGIN, by1 = fmaxf(oy, 0.f) + BOX_MARGIN;
 
-    int qn = 0;
+    int mine = 0;                   // candidates found by this lane
     float far2 = 0.f;
     bool hit = false;
+    unsigned* slot = maskbuf + lane;
     // 31 walls per pass: lane l handles vertex base+l, lanes 0..30 own wall (base+l, base+l+1)
-    for (int base = 0; base < V - 1; base += 31) {
+    for (int base = 0; base < V - 1; base += 31, slot += 32) {
         const int v = base + lane;
         const float2 pt = tv.line[min(v, V - 1)];
         const float ux = pt.x - s.x, uy = pt.y - s.y;
@@ -205,6 +215,8 @@ __device__ __forceinline__ ScanResult scan_fast(const TrackView& tv, const glg_r
         const float fb = fmaf(ux, nd.y, -(uy * nd.x));
         const float f = fmaf(atan2_approx(fb, fa), sect, fhalf);          // [0, O]
         const float m = fmaf(m_eps, rsqrt_fast(fmaxf(r2, 1e-12f)), m_eta);
+        const float nr = rintf(f);
+        const unsigned near = __ballot_sync(FULL, fabsf(f - nr) <= m);    // vertices on (the line of) a ray
         const float ux1 = __shfl_down_sync(FULL, ux, 1), uy1 = __shfl_down_sync(FULL, uy, 1);
         const float f1 = __shfl_down_sync(FULL, f, 1), m1 = __shfl_down_sync(FULL, m, 1);
         const float r21 = __shfl_down_sync(FULL, r2, 1);
@@ -242,32 +254,44 @@ __device__ __forceinline__ ScanResult scan_fast(const TrackView& tv, const glg_r
                     const unsigned run = (cnt >= 32) ? FULL : ((1u << cnt) - 1u);
                     mask = (st == 0) ? (run & all_rays) : (((run << st) | (run >> (O - st))) & all_rays);
                     // (b): an end point on the line of a ray also makes the opposite ray a candidate
-                    const float n0 = rintf(f), n1 = rintf(f1);
-                    if (fabsf(f - n0) <= m) { int r = (int)n0 + halfO; r = r >= O ? r - O : r; mask |= 1u << r; }
-                    if (fabsf(f1 - n1) <= m1) { int r = (int)n1 + halfO; r = r >= O ? r - O : r; mask |= 1u << r; }
+                    const unsigned nb = (near >> lane) & 3u;
+                    if (nb) {
+                        if (nb & 1u) { int r = (int)nr + halfO; r = r >= O ? r - O : r; mask |= 1u << r; }
+                        if (nb & 2u) { int r = (int)rintf(f1) + halfO; r = r >= O ? r - O : r; mask |= 1u << r; }
+                    }
                 }
             }
         }
-        // compact this pass's candidates into the queue (most lanes have none, few have one)
-        unsigned bal = __ballot_sync(FULL, mask != 0);
-        while (bal) {
-            const int cntb = __popc(bal);
-            if (qn + cntb > QUEUE_CAP) { queue_flush(tv, s, sc, qn); qn = 0; }
-            if (mask) {
-                const int i = __ffs(mask) - 1;
-                mask &= mask - 1;
-                sc->queue[qn + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)((v << 5) | i);
-            }
-            qn += cntb;
-            bal = __ballot_sync(FULL, mask != 0);
-        }
+        *slot = mask;
+        mine += __popc(mask);
     }
     far2 = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(far2)));       // far2 >= 0
     const float d2 = fmaf(nd.x, nd.x, nd.y * nd.y);
+    // ---- compact all (wall, ray) candidates of the car into the queue (exclusive prefix sum over lanes) ----
+    int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, off);
+        if (lane >= off) incl += t;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
     ScanResult res;
     res.wall_hit = __any_sync(FULL, hit);
-    res.safe = d2 > 0.5f && d2 < 2.f && far2 < 200.f * 200.f;
-    res.queued = qn;
+    res.safe = d2 > 0.5f && d2 < 2.f && far2 < 200.f * 200.f && total <= QUEUE_CAP;
+    res.queued = total;
+    if (res.safe && mine) {
+        int pos = incl - mine;
+        slot = maskbuf + lane;
+        for (int base = 0; base < V - 1; base += 31, slot += 32) {
+            unsigned mask = *slot;
+            const int v = base + lane;
+            while (mask) {
+                const int i = __ffs(mask) - 1;
+                mask &= mask - 1;
+                sc->queue[pos++] = (unsigned short)((v << 5) | i);
+            }
+        }
+    }
     return res;
 }
 
