@@ -93,6 +93,11 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
     } else {
         for (int i = threadIdx.x; i < 3 * N; i += blockDim.x) pts[i] = __ldg(&rec[i]);
     }
+    // Programmatic dependent launch: the geometry is never written by a step, so the copy above may
+    // overlap the tail of the previous kernel in the stream; everything below reads what that kernel
+    // (the previous step, or the policy that produced the actions) wrote and must wait for it.
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // ---- car state and kinematics while the copy is in flight (uniform across the warp) ----
     const int k = b * P + p;
@@ -274,17 +279,29 @@ static int check_step_args(const glg_race_params* pr, const float* geom, int B, 
     return GLG_OK;
 }
 
+template <int VARIANT, int OC>
+static void launch_one(const glg_race_params* pr, const StepArgs& a, cudaStream_t stream)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(a.B);
+    cfg.blockDim = dim3(32 * pr->num_players);
+    cfg.dynamicSmemBytes = smem_total(a.N, pr->num_players);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see griddepcontrol in the kernel
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, race_step_kernel<VARIANT, OC>, *pr, a);
+}
+
 static int launch_step(const glg_race_params* pr, const StepArgs& a, int variant, cudaStream_t stream)
 {
-    const int P = pr->num_players;
     if (variant == GLG_STEP_FAST && (pr->num_rays & 1)) variant = GLG_STEP_BRUTE;   // pruning pairs opposite rays
-    const size_t smem = smem_total(a.N, P);
-    if (variant == GLG_STEP_BRUTE)
-        race_step_kernel<GLG_STEP_BRUTE, 0><<<a.B, 32 * P, smem, stream>>>(*pr, a);
-    else if (pr->num_rays == 18)
-        race_step_kernel<GLG_STEP_FAST, 18><<<a.B, 32 * P, smem, stream>>>(*pr, a);
-    else
-        race_step_kernel<GLG_STEP_FAST, 0><<<a.B, 32 * P, smem, stream>>>(*pr, a);
+    if (variant == GLG_STEP_FAST && (2 * a.N - 1 + 30) / 31 > 32) variant = GLG_STEP_BRUTE;   // 32-bit pass bitmap
+    if (variant == GLG_STEP_BRUTE) launch_one<GLG_STEP_BRUTE, 0>(pr, a, stream);
+    else if (pr->num_rays == 18) launch_one<GLG_STEP_FAST, 18>(pr, a, stream);
+    else launch_one<GLG_STEP_FAST, 0>(pr, a, stream);
     return GLG_OK;
 }
 

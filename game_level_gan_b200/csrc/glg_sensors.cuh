@@ -169,8 +169,8 @@ struct ScanResult {
 };
 
 // OC: compile-time number of rays (0 = take it from pr at run time)
-// maskbuf: per-warp u32[maskbuf_len(N)]; slot pass*32+lane holds the candidate-ray mask of the wall that
-// lane owned in that pass (written and later re-read by the same lane).
+// maskbuf: per-warp u32[maskbuf_len(N)]; slot pass*32+lane holds the non-empty candidate-ray mask of the wall
+// that lane owned in that pass (written and later re-read by the same lane; `busy` remembers which passes).
 template <int OC>
 __device__ __forceinline__ ScanResult scan_fast(const TrackView& tv, const glg_race_params& pr, P2 s, P2 nd, P2 op,
                                                 bool need_col, SensorScratch* sc, unsigned* maskbuf)
@@ -200,12 +200,14 @@ __device__ __forceinline__ ScanResult scan_fast(const TrackView& tv, const glg_r
     const float by0 = fminf(oy, 0.f) - BOX_MARGIN, by1 = fmaxf(oy, 0.f) + BOX_MARGIN;
 
     int mine = 0;                   // candidates found by this lane
+    unsigned busy = 0;              // passes (<= 32, the host routes longer tracks to BRUTE) with candidates
     float far2 = 0.f;
     bool hit = false;
-    unsigned* slot = maskbuf + lane;
-    // 31 walls per pass: lane l handles vertex base+l, lanes 0..30 own wall (base+l, base+l+1)
-    for (int base = 0; base < V - 1; base += 31, slot += 32) {
-        const int v = base + lane;
+    const int passes = (V - 1 + 30) / 31;
+    // 31 walls per pass: lane l handles vertex 31*pass+l, lanes 0..30 own wall (v, v+1)
+#pragma unroll 1
+    for (int pass = 0; pass < passes; ++pass) {
+        const int v = pass * 31 + lane;
         const float2 pt = tv.line[min(v, V - 1)];
         const float ux = pt.x - s.x, uy = pt.y - s.y;
         const float r2 = fmaf(ux, ux, uy * uy);
@@ -262,8 +264,11 @@ __device__ __forceinline__ ScanResult scan_fast(const TrackView& tv, const glg_r
                 }
             }
         }
-        *slot = mask;
-        mine += __popc(mask);
+        if (mask) {
+            maskbuf[pass * 32 + lane] = mask;
+            busy |= 1u << pass;
+            mine += __popc(mask);
+        }
     }
     far2 = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(far2)));       // far2 >= 0
     const float d2 = fmaf(nd.x, nd.x, nd.y * nd.y);
@@ -281,10 +286,11 @@ __device__ __forceinline__ ScanResult scan_fast(const TrackView& tv, const glg_r
     res.queued = total;
     if (res.safe && mine) {
         int pos = incl - mine;
-        slot = maskbuf + lane;
-        for (int base = 0; base < V - 1; base += 31, slot += 32) {
-            unsigned mask = *slot;
-            const int v = base + lane;
+        while (busy) {
+            const int pass = __ffs(busy) - 1;
+            busy &= busy - 1;
+            unsigned mask = maskbuf[pass * 32 + lane];
+            const int v = pass * 31 + lane;
             while (mask) {
                 const int i = __ffs(mask) - 1;
                 mask &= mask - 1;
