@@ -354,9 +354,11 @@ def main():
     ap.add_argument('--variant', default='fast', choices=['fast', 'brute'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--replicas', type=int, default=REPLICAS, help='independent config-2 batches stepped round-robin')
+    ap.add_argument('--tracks', type=int, default=4096, help='tracks per batch (default = config 2)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
+    globals()['B_TRACKS'] = args.tracks
     if args.impl == 'reference':
         if args.steps > 400:
             args.steps = 200          # bounded: ~0.1 s per sampled step on the host

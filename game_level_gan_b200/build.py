@@ -31,11 +31,12 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return OUT
+    extra = os.environ.get('GLG_NVCC_EXTRA', '').split()
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace('.cu', '.o'))
-        cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [NVCC] + FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
         objs.append(obj)
     failed = False

@@ -69,8 +69,12 @@ __device__ __forceinline__ void record_copy_wait(uint64_t* bar) {
 }
 
 // OC: number of rays known at compile time (0 = generic)
+#ifndef GLG_STEP_MINBLOCKS
+#define GLG_STEP_MINBLOCKS 4     // 256-thread blocks per SM the register allocator targets (4 -> 64 registers)
+#endif
+
 template <int VARIANT, int OC>
-__global__ void __launch_bounds__(32 * GLG_MAX_PLAYERS, 4)
+__global__ void __launch_bounds__(32 * GLG_MAX_PLAYERS, GLG_STEP_MINBLOCKS)
 race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
