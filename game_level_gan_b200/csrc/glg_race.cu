@@ -25,6 +25,7 @@ struct StepArgs {
     const float* geom;
     const int64_t* actions;
     const uint8_t* valid;
+    const float* extent;
     glg_race_state st;
     float* states_out;
     float* rewards_out;
@@ -91,7 +92,7 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + smem_barrier_offset(N));
     const uint32_t rec_bytes = (uint32_t)(3 * N * sizeof(float2));
     // one elected thread issues a single bulk copy when the record is 16-byte granular (N even)
-    const bool bulk = VARIANT == GLG_STEP_FAST && (rec_bytes & 15u) == 0 && ((uintptr_t)a.geom & 15u) == 0;
+    const bool bulk = VARIANT != GLG_STEP_BRUTE && (rec_bytes & 15u) == 0 && ((uintptr_t)a.geom & 15u) == 0;
     if (bulk) {
         if (threadIdx.x == 0) record_copy_async(pts, rec, rec_bytes, bar);
     } else {
@@ -108,6 +109,8 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
     bool alive = a.st.alive[k] != 0;
     bool fin = a.st.finishes[k] != 0;
     const bool ok = a.valid[b] != 0;
+    float2 ext = make_float2(0.f, 0.f);
+    if (VARIANT == GLG_STEP_FAST) ext = __ldg(reinterpret_cast<const float2*>(a.extent) + b);
     int act = (int)a.actions[(size_t)p * B + b];
     act = min(max(act, 0), 8);
     if (!alive || !ok) act = 0;                                           // race.py:359
@@ -177,6 +180,8 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
     const bool upd = alive && moving && ok;                                // race.py:380
     ScanResult scan{false, true, 0};
     if (VARIANT == GLG_STEP_FAST) {
+        if (alive) scan = scan_two_stage(tv, pr, np, nd, op, upd, scratch, reinterpret_cast<unsigned short*>(maskbuf), ext.x, ext.y);
+    } else if (VARIANT == GLG_STEP_SCAN) {
         if (alive) scan = scan_fast<OC>(tv, pr, np, nd, op, upd, scratch, maskbuf);
     } else if (upd) {
         scan.wall_hit = collide_brute(tv, op, np);
@@ -224,8 +229,8 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
     // lane i < O: clamp(t_i, max)/max; lane O: speed/vmax (:497); lane O+1: idx/3 (:376) - one division
     float num = 0.f, den = 1.f;
     if (alive) {
-        const float t = (VARIANT == GLG_STEP_FAST) ? sensors_finish(tv, pr, np, nd, scratch, scan, O)
-                                                   : sensors_brute(tv, pr, np, nd);
+        const float t = (VARIANT != GLG_STEP_BRUTE) ? sensors_finish(tv, pr, np, nd, scratch, scan, O)
+                                                    : sensors_brute(tv, pr, np, nd);
         num = (t != t) ? t : fminf(t, pr.max_distance);                    // NaN propagates like torch.clamp
         den = pr.max_distance;
     }
@@ -270,8 +275,13 @@ __global__ void winner_stats_kernel(const int64_t* __restrict__ winners, int tri
 }
 
 static int check_step_args(const glg_race_params* pr, const float* geom, int B, int N, const void* actions,
-                           const void* valid, const glg_race_state& st, const void* so, const void* ro)
+                           const void* valid, const void* extent, int variant, const glg_race_state& st,
+                           const void* so, const void* ro)
 {
+    GLG_REQUIRE(variant == GLG_STEP_FAST || variant == GLG_STEP_BRUTE || variant == GLG_STEP_SCAN,
+                "glg_race_step: unknown variant %d", variant);
+    GLG_REQUIRE(variant != GLG_STEP_FAST || extent != nullptr || B == 0,
+                "glg_race_step: GLG_STEP_FAST needs the track extents (glg_track_extent)");
     GLG_REQUIRE(pr != nullptr, "glg_race_step: params is null");
     GLG_REQUIRE(pr->num_players >= 1 && pr->num_players <= GLG_MAX_PLAYERS, "glg_race_step: num_players %d out of range", pr->num_players);
     GLG_REQUIRE(pr->num_rays >= 1 && pr->num_rays <= GLG_MAX_RAYS, "glg_race_step: num_rays %d out of range", pr->num_rays);
@@ -301,11 +311,13 @@ static void launch_one(const glg_race_params* pr, const StepArgs& a, cudaStream_
 
 static int launch_step(const glg_race_params* pr, const StepArgs& a, int variant, cudaStream_t stream)
 {
-    if (variant == GLG_STEP_FAST && (pr->num_rays & 1)) variant = GLG_STEP_BRUTE;   // pruning pairs opposite rays
-    if (variant == GLG_STEP_FAST && (2 * a.N - 1 + 30) / 31 > 32) variant = GLG_STEP_BRUTE;   // 32-bit pass bitmap
+    if (variant == GLG_STEP_FAST && pr->num_rays != 18) variant = GLG_STEP_SCAN;    // stage 1 is written for 9 ray lines
+    if (variant == GLG_STEP_SCAN && (pr->num_rays & 1)) variant = GLG_STEP_BRUTE;   // pruning pairs opposite rays
+    if (variant == GLG_STEP_SCAN && (2 * a.N - 1 + 30) / 31 > 32) variant = GLG_STEP_BRUTE;   // 32-bit pass bitmap
     if (variant == GLG_STEP_BRUTE) launch_one<GLG_STEP_BRUTE, 0>(pr, a, stream);
-    else if (pr->num_rays == 18) launch_one<GLG_STEP_FAST, 18>(pr, a, stream);
-    else launch_one<GLG_STEP_FAST, 0>(pr, a, stream);
+    else if (variant == GLG_STEP_FAST) launch_one<GLG_STEP_FAST, 18>(pr, a, stream);
+    else if (pr->num_rays == 18) launch_one<GLG_STEP_SCAN, 18>(pr, a, stream);
+    else launch_one<GLG_STEP_SCAN, 0>(pr, a, stream);
     return GLG_OK;
 }
 
@@ -324,33 +336,32 @@ extern "C" int glg_race_init(glg_race_state st, int32_t B, int32_t P, int32_t* a
 }
 
 extern "C" int glg_race_step(const glg_race_params* params, const float* geom, int32_t B, int32_t N,
-                             const int64_t* actions, const uint8_t* valid, glg_race_state state,
+                             const int64_t* actions, const uint8_t* valid, const float* extent, glg_race_state state,
                              int32_t step_no, float* states_out, float* rewards_out,
                              int32_t* alive_stamp, float* history, int32_t record_id,
                              int32_t variant, glg_stream_t stream)
 {
     using namespace glg;
-    const int rc = check_step_args(params, geom, B, N, actions, valid, state, states_out, rewards_out);
+    const int rc = check_step_args(params, geom, B, N, actions, valid, extent, variant, state, states_out, rewards_out);
     if (rc != GLG_OK || B == 0) return rc;
-    GLG_REQUIRE(variant == GLG_STEP_FAST || variant == GLG_STEP_BRUTE, "glg_race_step: unknown variant %d", variant);
-    StepArgs a{geom, actions, valid, state, states_out, rewards_out, alive_stamp, history, B, N, step_no, record_id};
+    StepArgs a{geom, actions, valid, extent, state, states_out, rewards_out, alive_stamp, history, B, N, step_no, record_id};
     launch_step(params, a, variant, (cudaStream_t)stream);
     return launch_status("glg_race_step");
 }
 
 extern "C" int glg_race_rollout(const glg_race_params* params, const float* geom, int32_t B, int32_t N,
-                                const int64_t* actions, int32_t T, const uint8_t* valid, glg_race_state state,
+                                const int64_t* actions, int32_t T, const uint8_t* valid, const float* extent,
+                                glg_race_state state,
                                 int32_t first_step_no, float* states_out, float* rewards_out, int32_t keep_all,
                                 int32_t* alive_stamp, int32_t variant, glg_stream_t stream)
 {
     using namespace glg;
-    const int rc = check_step_args(params, geom, B, N, actions, valid, state, states_out, rewards_out);
+    const int rc = check_step_args(params, geom, B, N, actions, valid, extent, variant, state, states_out, rewards_out);
     if (rc != GLG_OK || B == 0 || T <= 0) return rc;
-    GLG_REQUIRE(variant == GLG_STEP_FAST || variant == GLG_STEP_BRUTE, "glg_race_rollout: unknown variant %d", variant);
     const size_t PB = (size_t)params->num_players * B;
     const size_t W = params->num_rays + 2;
     for (int t = 0; t < T; ++t) {
-        StepArgs a{geom, actions + (size_t)t * PB, valid, state,
+        StepArgs a{geom, actions + (size_t)t * PB, valid, extent, state,
                    keep_all ? states_out + (size_t)t * PB * W : states_out,
                    keep_all ? rewards_out + (size_t)t * PB : rewards_out,
                    alive_stamp, nullptr, B, N, first_step_no + t, -1};

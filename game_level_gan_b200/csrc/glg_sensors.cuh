@@ -8,11 +8,15 @@
 // parameter t given by the reference formula.
 //
 //   BRUTE : every ray x every wall and every wall x path with the literal formula.
-//   FAST  : one pass over the polyline vertices that (1) bins every vertex into the angular sector
+//   SCAN  : one pass over the polyline vertices that (1) bins every vertex into the angular sector
 //           between two rays and emits only the (wall, ray) pairs that can possibly hit, (2) tests the
 //           wall's box against the car's path box; candidates of both kinds are then evaluated with
 //           the SAME literal formula, so every number that is reported comes out of the reference's
 //           arithmetic.  See the comment at scan_fast for why the pruning is exact.
+//   FAST  : two stages.  Stage 1 is a cheap pass over the vertices that only decides WHETHER a wall can
+//           meet any ray line (sign of Im z^(O/2), z = vertex in the car frame, which vanishes exactly on
+//           the O/2 ray lines) and flags the few walls near the path; stage 2 runs the SCAN analysis on
+//           the flagged walls only (one wall per lane).  See scan_two_stage.
 #pragma once
 #include "glg_common.cuh"
 #include "glg_exact.cuh"
@@ -30,12 +34,18 @@ struct SensorScratch {           // per-warp shared memory (fixed part)
 };
 
 // shared memory carve-up of the step kernel:
-//   [record 3N float2][mbarrier 16 B][P x SensorScratch][P x maskbuf(2N u32, padded to 32)]
+//   [record 3N float2][mbarrier 16 B][P x SensorScratch][P x maskbuf_len(N) u32]
 __host__ __device__ inline size_t smem_barrier_offset(int N) {
     return ((size_t)3 * N * sizeof(float2) + 15) & ~(size_t)15;
 }
 __host__ __device__ inline size_t smem_scratch_offset(int N) { return smem_barrier_offset(N) + 16; }
-__host__ __device__ inline int maskbuf_len(int N) { return ((2 * N + 31) / 31 + 1) * 32; }
+// per-warp u32 scratch: SCAN keeps one candidate-ray mask per (pass, lane); FAST keeps two u16 lists of
+// wall indices (sensor walls, collision walls) of list_len(N) entries each
+__host__ __device__ inline int list_len(int N) { return ((2 * N + 31) / 32) * 32; }
+__host__ __device__ inline int maskbuf_len(int N) {
+    const int a = ((2 * N + 31) / 31 + 1) * 32, b = list_len(N);      // b u32 = 2 lists of b u16
+    return a > b ? a : b;
+}
 __host__ __device__ inline size_t smem_maskbuf_offset(int N, int P) {
     return smem_scratch_offset(N) + (size_t)P * sizeof(SensorScratch);
 }
@@ -298,6 +308,215 @@ __device__ __forceinline__ ScanResult scan_fast(const TrackView& tv, const glg_r
             }
         }
     }
+    return res;
+}
+
+
+// ---- FAST: two-stage scan ---------------------------------------------------------------------
+// Stage 1 (all 2N vertices, ~30 instructions each): with z = (u . nd) + i (u x nd), u = vertex - s, the
+// O/2 ray LINES of the car are exactly the zero set of Im z^(O/2) (= |z|^(O/2) sin((O/2) phi)).
+// A wall whose end points are farther than Rc = 3.2 Lmax from the car (Lmax = longest wall of the track,
+// glg_track_extent) subtends less than 18 degrees < one sector, so it meets a ray line iff the sign of
+// Im z^9 differs at its end points; "near a ray line" (perpendicular distance <= EPS_PERP, the bound of
+// the reference's own fp32 sign noise, see scan_fast) is |Im z^9| <= 9 EPS_PERP |nd| |z|^8 because
+// |sin 9x| <= 9 |sin x|.  A wall is FLAGGED if the sign differs, or an end point is near a ray line, or an
+// end point is closer than Rc.  An unflagged wall has both end points strictly on one side of every ray
+// line, farther than EPS_PERP from it, and the car is outside the wall's box: o3 == o4 != 0 for every
+// ray, so no case of games/race.py:248-269 can fire - it yields +inf for all rays, exactly what
+// dropping it does.  Evaluation error of Im z^9 in fp32 is < 1e-6 |z|^9, i.e. < 1e-7 r in perpendicular
+// distance (r <= 200): two orders below EPS_PERP.
+// Collision walls: boxes (each widened by BOX_MARGIN) can only meet if the wall's first end point is
+// within |path|_1 + Lmax + 1e-3 of s.
+// Stage 2: flagged walls, one per lane, get the full analysis of scan_fast (sector of both end points
+// with margins, short-way span, opposite rays, car-on-the-wall's-line case) and emit (wall, ray) pairs.
+constexpr float RC_FACTOR = 3.2f;          // 1 / (2 sin(alpha/2)) for alpha = 17.98 deg < 20 deg = one sector at O = 18
+
+struct WallRays { unsigned mask; };
+
+__device__ __forceinline__ unsigned wall_ray_mask(float ux, float uy, float ux1, float uy1, P2 nd, int O,
+                                                  float sect, float fhalf, float m_eps, float m_eta, unsigned all_rays)
+{
+    const float fO = (float)O;
+    const int halfO = O >> 1;
+    const float r2 = fmaf(ux, ux, uy * uy), r21 = fmaf(ux1, ux1, uy1 * uy1);
+    const float fa = fmaf(ux, nd.x, uy * nd.y), fb = fmaf(ux, nd.y, -(uy * nd.x));
+    const float fa1 = fmaf(ux1, nd.x, uy1 * nd.y), fb1 = fmaf(ux1, nd.y, -(uy1 * nd.x));
+    const float f = fmaf(atan2_approx(fb, fa), sect, fhalf);
+    const float f1 = fmaf(atan2_approx(fb1, fa1), sect, fhalf);
+    const float m = fmaf(m_eps, rsqrt_fast(fmaxf(r2, 1e-12f)), m_eta);
+    const float m1 = fmaf(m_eps, rsqrt_fast(fmaxf(r21, 1e-12f)), m_eta);
+    const float cr = fmaf(ux, uy1, -(uy * ux1));                       // cross(u_p, u_q)
+    const float tau = fmaf(5e-7f, r2 + r21, 2e-6f);
+    const float mm = fmaxf(m, m1);
+    if (fabsf(cr) <= tau || mm > 0.45f) return all_rays;               // (c), or a point almost at the car
+    const float lo = cr > 0.f ? f1 : f;
+    float hi = cr > 0.f ? f : f1;
+    hi = hi < lo ? hi + fO : hi;                                       // wrap through f = O == 0
+    const int ilo = __float2int_ru(lo - mm), ihi = __float2int_rd(hi + mm);
+    int cnt = ihi - ilo + 1;                                           // rays inside the widened span
+    if (cnt <= 0) return 0u;
+    cnt = min(cnt, O);
+    const int st = ilo >= O ? ilo - O : ilo;                           // ilo in [0, O]
+    const unsigned run = (cnt >= 32) ? FULL : ((1u << cnt) - 1u);
+    unsigned mask = (st == 0) ? (run & all_rays) : (((run << st) | (run >> (O - st))) & all_rays);
+    const float nr = rintf(f), nr1 = rintf(f1);
+    if (fabsf(f - nr) <= m) { int r = (int)nr + halfO; r = r >= O ? r - O : r; mask |= 1u << r; }     // (b)
+    if (fabsf(f1 - nr1) <= m1) { int r = (int)nr1 + halfO; r = r >= O ? r - O : r; mask |= 1u << r; }
+    return mask;
+}
+
+// lists: per-warp u16[2 * list_len(N)] (sensor walls, then collision walls).  extent = {Rb, Lmax} of the track.
+__device__ __forceinline__ ScanResult scan_two_stage(const TrackView& tv, const glg_race_params& pr, P2 s, P2 nd, P2 op,
+                                                     bool need_col, SensorScratch* sc, unsigned short* lists,
+                                                     float Rb, float Lmax)
+{
+    constexpr int O = 18;
+    const int lane = lane_id();
+    const int N = tv.N;
+    const int V = 2 * N;
+    const unsigned all_rays = (1u << O) - 1u;
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned short* wlist = lists;
+    unsigned short* clist = lists + list_len(N);
+
+    ScanResult res{false, false, 0};
+    const float d2 = fmaf(nd.x, nd.x, nd.y * nd.y);
+    // preconditions of the pruning (see scan_fast): heading norm, every point within 200 units of the car
+    if (!(d2 > 0.5f && d2 < 2.f && fabsf(s.x) + fabsf(s.y) + Rb < 200.f)) {
+        if (need_col) res.wall_hit = collide_brute(tv, op, s);
+        return res;
+    }
+    if (lane < O) {
+        P2 d, f;
+        ray_setup(pr, lane, s, nd, d, f);
+        sc->ray[lane] = make_float4(d.x, d.y, f.x, f.y);
+        sc->tmin[lane] = 0x7f800000;
+    }
+    if (lane == 0) sc->nan_mask = 0;
+
+    // ---- stage 1 ----
+    // Lmax excludes the start line (wall N-1, as long as the track is wide): it is appended to both lists below.
+    const float Rc = fmaf(RC_FACTOR, Lmax, 1e-3f);
+    const float close2 = Rc * Rc * d2 * 1.0001f;                       // thresholds on |z|^2 = r^2 d2
+    const float colR = fabsf(op.x - s.x) + fabsf(op.y - s.y) + Lmax + 1e-3f;
+    const float col2 = need_col ? colR * colR * d2 * 1.0001f : -1.f;
+    const float Kn = 9.f * EPS_PERP * 1.4143f * 1.001f;                // 9 EPS_PERP |nd| with |nd| < sqrt(2)
+    const int passes = (V + 31) / 32;                                  // <= 32 (N <= 512)
+    // lane l handles vertices l, l+32, ...; bit `pass` of sbits / fbits / cbits describes vertex 32*pass + l
+    unsigned sbits = 0, fbits = 0, cbits = 0;
+#pragma unroll 3
+    for (int pass = 0; pass < passes; ++pass) {
+        const int v = pass * 32 + lane;
+        const float2 pt = tv.line[min(v, V - 1)];
+        const float ux = pt.x - s.x, uy = pt.y - s.y;
+        const float a = fmaf(ux, nd.x, uy * nd.y);
+        const float b = fmaf(ux, nd.y, -(uy * nd.x));
+        const float a2 = a * a, b2 = b * b;
+        const float r2z = a2 + b2;
+        const float re3 = a * fmaf(-3.f, b2, a2);                      // z^3
+        const float im3 = b * fmaf(3.f, a2, -b2);
+        const float im9 = im3 * fmaf(3.f, re3 * re3, -(im3 * im3));    // Im (z^3)^3
+        const float r4 = r2z * r2z;
+        const unsigned bit = 1u << pass;
+        if (im9 < 0.f) sbits |= bit;
+        if (fabsf(im9) <= Kn * (r4 * r4) || r2z <= close2) fbits |= bit;
+        if (r2z <= col2) cbits |= bit;
+    }
+    // wall w = (vertex w, vertex w+1): the next vertex lives in lane+1 (same pass), or in lane 0 of the next pass
+    unsigned s1 = __shfl_down_sync(FULL, sbits, 1), f1 = __shfl_down_sync(FULL, fbits, 1);
+    const unsigned s0 = __shfl_sync(FULL, sbits, 0), f0 = __shfl_sync(FULL, fbits, 0);
+    if (lane == 31) { s1 = s0 >> 1; f1 = f0 >> 1; }
+    // walls owned by this lane: w = 32*pass + lane <= V-2, except the start line w = N-1
+    const int nown = (V - 2 - lane >= 0) ? ((V - 2 - lane) >> 5) + 1 : 0;
+    unsigned own = nown >= 32 ? FULL : ((1u << nown) - 1u);
+    if (((N - 1) & 31) == lane) own &= ~(1u << ((N - 1) >> 5));
+    unsigned wbits = ((sbits ^ s1) | fbits | f1) & own;
+    cbits &= own;
+    int nw, nc = 0;
+    {   // exclusive prefix sum of the per-lane counts, then every lane appends its own walls
+        const int cnt = __popc(wbits);
+        int incl = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, off);
+            if (lane >= off) incl += t;
+        }
+        nw = __shfl_sync(FULL, incl, 31);
+        int pos = incl - cnt;
+        while (wbits) {
+            const int pass = __ffs(wbits) - 1;
+            wbits &= wbits - 1;
+            wlist[pos++] = (unsigned short)(pass * 32 + lane);
+        }
+        if (lane == 0) wlist[nw] = (unsigned short)(N - 1);            // the start line, always
+        ++nw;
+    }
+    if (need_col) {
+        unsigned live = __ballot_sync(FULL, cbits != 0u);
+        while (live) {                                                 // usually zero or one round
+            if (cbits) {
+                const int pass = __ffs(cbits) - 1;
+                cbits &= cbits - 1;
+                clist[nc + __popc(live & lt)] = (unsigned short)(pass * 32 + lane);
+            }
+            nc += __popc(live);
+            live = __ballot_sync(FULL, cbits != 0u);
+        }
+        if (lane == 0) clist[nc] = (unsigned short)(N - 1);
+        ++nc;
+    }
+    __syncwarp();
+
+    // ---- collision: exact test of the walls near the path (race.py:406) ----
+    if (nc) {
+        const float ox = op.x - s.x, oy = op.y - s.y;
+        const float bx0 = fminf(ox, 0.f) - BOX_MARGIN, bx1 = fmaxf(ox, 0.f) + BOX_MARGIN;
+        const float by0 = fminf(oy, 0.f) - BOX_MARGIN, by1 = fmaxf(oy, 0.f) + BOX_MARGIN;
+        bool hit = false;
+        for (int e = lane; e < nc; e += 32) {
+            const int w = clist[e];
+            const float2 p0 = tv.line[w], p1 = tv.line[w + 1];
+            const float ux = p0.x - s.x, uy = p0.y - s.y, ux1 = p1.x - s.x, uy1 = p1.y - s.y;
+            if (!(fmaxf(ux, ux1) < bx0 || fminf(ux, ux1) > bx1 || fmaxf(uy, uy1) < by0 || fminf(uy, uy1) > by1)) {
+                P2 p, q;
+                wall_by_line_index(tv, w, p, q);
+                hit = hit || segments_cross(p, q, op, s);
+            }
+        }
+        res.wall_hit = __any_sync(FULL, hit);
+    }
+
+    // ---- stage 2: candidate rays of the flagged walls ----
+    const float sect = (float)O * (0.5f / PI_F);
+    const float m_eta = ETA_ANGLE * sect, m_eps = EPS_PERP * sect, fhalf = 0.5f * (float)O;
+    int total = 0;
+    bool overflow = false;
+    for (int base = 0; base < nw; base += 32) {
+        const int e = base + lane;
+        unsigned mask = 0;
+        int w = 0;
+        if (e < nw) {
+            w = wlist[e];
+            const float2 p0 = tv.line[w], p1 = tv.line[w + 1];
+            mask = wall_ray_mask(p0.x - s.x, p0.y - s.y, p1.x - s.x, p1.y - s.y, nd, O, sect, fhalf, m_eps, m_eta, all_rays);
+        }
+        // emit one ray of every lane per round (most walls have exactly one)
+        unsigned live = __ballot_sync(FULL, mask != 0u);
+        while (live) {
+            const int cnt = __popc(live);
+            if (total + cnt > QUEUE_CAP) { overflow = true; break; }
+            if (mask) {
+                const int i = __ffs(mask) - 1;
+                mask &= mask - 1;
+                sc->queue[total + __popc(live & lt)] = (unsigned short)((w << 5) | i);
+            }
+            total += cnt;
+            live = __ballot_sync(FULL, mask != 0u);
+        }
+        if (overflow) break;
+    }
+    res.safe = !overflow;
+    res.queued = total;
     return res;
 }
 

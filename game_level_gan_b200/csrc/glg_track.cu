@@ -2,6 +2,8 @@
 //
 //   glg_track_build    replaces games/race.py:126-158  (Race.reset, geometry part)
 //   glg_track_validate replaces games/race.py:326-334  (Race._is_correct) as used at :199-200
+//   glg_track_extent   per-track bounding radius / longest wall (no reference counterpart; the
+//                      step kernel's exact pruning needs both, csrc/glg_sensors.cuh)
 //
 // HBM layout of the result: one record {right[N] reversed, left[N], centre[N]} of float2 per track
 // (include/glg_b200.h, glg_common.cuh TrackView).  Both kernels are "reset-time" work, amortised over hundreds of steps.
@@ -143,7 +145,52 @@ __global__ void track_validate_kernel(const float* __restrict__ geom, int B, int
     if (threadIdx.x == 0) valid[b] = bad_flag ? 0 : 1;
 }
 
+// One warp per track: extent[b] = { max |point| over the record, max wall length of the polyline except the start line },
+// both rounded UP (they are used as conservative bounds).  A record with a non-finite coordinate
+// gets +inf / +inf, which makes every car of that track take the unpruned path.
+__global__ void track_extent_kernel(const float* __restrict__ geom, int B, int N, float* __restrict__ extent)
+{
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const int lane = lane_id();
+    const float2* rec = reinterpret_cast<const float2*>(geom) + (size_t)b * 3 * N;
+    float r2 = 0.f, l2 = 0.f;
+    bool finite = true;
+    for (int j = lane; j < 3 * N; j += 32) {
+        const float2 p = __ldg(&rec[j]);
+        const float q = fmaf(p.x, p.x, p.y * p.y);
+        finite = finite && (q <= 3e38f);                  // false for NaN and inf
+        r2 = fmaxf(r2, q);
+        if (j + 1 < 2 * N && j != N - 1) {                // wall j of the polyline; the start line (N-1) is not counted
+            const float2 n = __ldg(&rec[j + 1]);
+            const float dx = n.x - p.x, dy = n.y - p.y;
+            l2 = fmaxf(l2, fmaf(dx, dx, dy * dy));
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        r2 = fmaxf(r2, __shfl_xor_sync(FULL, r2, off));
+        l2 = fmaxf(l2, __shfl_xor_sync(FULL, l2, off));
+    }
+    finite = __all_sync(FULL, finite);
+    if (lane == 0) {
+        const float up = 1.000001f;
+        extent[2 * b] = finite ? __fsqrt_ru(r2) * up : INF;
+        extent[2 * b + 1] = finite ? __fsqrt_ru(l2) * up : INF;
+    }
+}
+
 }  // namespace glg
+
+extern "C" int glg_track_extent(const float* geom, int32_t B, int32_t N, float* extent, glg_stream_t stream)
+{
+    using namespace glg;
+    GLG_REQUIRE(B >= 0 && N >= 2 && N <= 512, "glg_track_extent: need B >= 0 and 2 <= N <= 512 (got B=%d N=%d)", B, N);
+    GLG_REQUIRE((B == 0) || (geom && extent), "glg_track_extent: null pointer");
+    if (B == 0) return GLG_OK;
+    track_extent_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(geom, B, N, extent);
+    return launch_status("glg_track_extent");
+}
 
 extern "C" int glg_track_build(const float* tracks, int32_t B, int32_t L, const float* sin_table,
                                const float* cos_table, int32_t table_half, float* geom,

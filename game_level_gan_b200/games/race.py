@@ -104,7 +104,7 @@ class Race(MultiEnvironment):
         return self._const[key]
 
     def _variant_code(self):
-        return {'fast': _lib.STEP_FAST, 'brute': _lib.STEP_BRUTE}[self.variant]
+        return {'fast': _lib.STEP_FAST, 'brute': _lib.STEP_BRUTE, 'scan': _lib.STEP_SCAN}[self.variant]
 
     # ---- reference API -------------------------------------------------------------------------
     def state_shape(self):
@@ -156,6 +156,8 @@ class Race(MultiEnvironment):
             self._valid_tracks = torch.empty((B,), dtype=torch.uint8, device=dev)
             check(lib.glg_track_validate(ptr(self._geom), B, N, ptr(self._valid_tracks), stream),
                   'glg_track_validate')
+            self._extent = torch.empty((B, 2), dtype=torch.float32, device=dev)
+            check(lib.glg_track_extent(ptr(self._geom), B, N, ptr(self._extent), stream), 'glg_track_extent')
             self.positions = torch.empty((B, P, 2), dtype=torch.float32, device=dev)
             self.directions = torch.empty((B, P, 2), dtype=torch.float32, device=dev)
             self.speeds = torch.empty((B, P), dtype=torch.float32, device=dev)
@@ -202,7 +204,7 @@ class Race(MultiEnvironment):
                 self._hist_steps.append(self.steps)
             check(_lib.lib().glg_race_step(
                 self._params, ptr(self._geom), B, self._geom.size(2), ptr(actions), ptr(self._valid_tracks),
-                self._state, self.steps, ptr(states), ptr(rewards), ptr(self._stamp), ptr(hist),
+                ptr(self._extent), self._state, self.steps, ptr(states), ptr(rewards), ptr(self._stamp), ptr(hist),
                 self.record_id, self._variant_code(), _lib.stream_ptr(dev)), 'glg_race_step')
             self._alive_known = None
             return states, rewards
@@ -222,7 +224,7 @@ class Race(MultiEnvironment):
             rewards = torch.empty(shape_r, dtype=torch.float32, device=dev)
             check(_lib.lib().glg_race_rollout(
                 self._params, ptr(self._geom), B, self._geom.size(2), ptr(actions), T, ptr(self._valid_tracks),
-                self._state, self.steps + 1, ptr(states), ptr(rewards), int(keep_all), ptr(self._stamp),
+                ptr(self._extent), self._state, self.steps + 1, ptr(states), ptr(rewards), int(keep_all), ptr(self._stamp),
                 self._variant_code(), _lib.stream_ptr(dev)), 'glg_race_rollout')
             self.steps += T
             self._alive_known = None

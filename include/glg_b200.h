@@ -31,8 +31,9 @@ extern "C" {
 #define GLG_ALIVE_SLOTS   64  /* int32 slots of the "somebody is alive" step stamp            */
 
 /* step kernel variants (all produce identical results; tests compare them) */
-#define GLG_STEP_FAST     0   /* exact angular pruning of the ray cast (production)            */
+#define GLG_STEP_FAST     0   /* two-stage exact pruning of the ray cast (production; 18 rays)   */
 #define GLG_STEP_BRUTE    1   /* every ray x every wall, the literal reference loop            */
+#define GLG_STEP_SCAN     2   /* single-pass exact angular pruning (any even number of rays)   */
 
 typedef void* glg_stream_t;   /* cudaStream_t */
 
@@ -103,6 +104,12 @@ int glg_track_build(const float* tracks, int32_t B, int32_t L,
  *   valid [B] u8 out                                                                         */
 int glg_track_validate(const float* geom, int32_t B, int32_t N, uint8_t* valid, glg_stream_t stream);
 
+/* Conservative per-track bounds the production step kernel prunes with (no reference counterpart):
+ *   extent [B,2] f32 out = { max |point| over the record, longest wall of the polyline (the start
+ *   line excepted) }, rounded up;
+ *   +inf for a record with non-finite coordinates (its cars then take the unpruned path).      */
+int glg_track_extent(const float* geom, int32_t B, int32_t N, float* extent, glg_stream_t stream);
+
 /* Initial car state (games/race.py:182-190) and a cleared alive stamp.                        */
 int glg_race_init(glg_race_state state, int32_t B, int32_t P, int32_t* alive_stamp, glg_stream_t stream);
 
@@ -111,15 +118,16 @@ int glg_race_init(glg_race_state state, int32_t B, int32_t P, int32_t* alive_sta
  * sensors, observation pack.
  *   actions    [P,B] i64 (values 0..8), not modified
  *   valid      [B] u8 (per track)
+ *   extent     [B,2] f32 from glg_track_extent (required by GLG_STEP_FAST, else may be NULL)
  *   step_no    value of Race.steps AFTER the increment of this step (race.py:349)
  *   states_out [P,B,num_rays+2] f32, rewards_out [P,B] f32
  *   alive_stamp [GLG_ALIVE_SLOTS] i32 or NULL: slot (b % 64) := step_no if track b still has an
  *              alive car after this step (host reads it for Race.finished(), race.py:502-504)
  *   history    optional [>= step_no+1, P, 6] f32 ring written for track `record_id`
  *              (x, y, dx, dy, masked action, alive) at row step_no (race.py:492-494), or NULL
- *   variant    GLG_STEP_FAST or GLG_STEP_BRUTE                                                */
+ *   variant    GLG_STEP_FAST, GLG_STEP_SCAN or GLG_STEP_BRUTE (identical results)                */
 int glg_race_step(const glg_race_params* params, const float* geom, int32_t B, int32_t N,
-                  const int64_t* actions, const uint8_t* valid, glg_race_state state,
+                  const int64_t* actions, const uint8_t* valid, const float* extent, glg_race_state state,
                   int32_t step_no, float* states_out, float* rewards_out,
                   int32_t* alive_stamp, float* history, int32_t record_id,
                   int32_t variant, glg_stream_t stream);
@@ -128,8 +136,8 @@ int glg_race_step(const glg_race_params* params, const float* geom, int32_t B, i
  * Launches T step kernels back to back on `stream`; states_out/rewards_out hold the LAST step's
  * outputs, or all steps if `keep_all` (then [T,P,B,W] / [T,P,B]).  first_step_no as in glg_race_step. */
 int glg_race_rollout(const glg_race_params* params, const float* geom, int32_t B, int32_t N,
-                     const int64_t* actions, int32_t T, const uint8_t* valid, glg_race_state state,
-                     int32_t first_step_no, float* states_out, float* rewards_out, int32_t keep_all,
+                     const int64_t* actions, int32_t T, const uint8_t* valid, const float* extent,
+                     glg_race_state state, int32_t first_step_no, float* states_out, float* rewards_out, int32_t keep_all,
                      int32_t* alive_stamp, int32_t variant, glg_stream_t stream);
 
 /* Winner per track.  Replaces Race.winners, games/race.py:506-529.  winners [B] i64 out.      */
