@@ -19,6 +19,27 @@ int launch_status(const char* what);
         }                                        \
     } while (0)
 
+// Optional per-phase cycle accounting of the step kernel (scratch builds with -DGLG_PHASE_CLOCKS only):
+// lane 0 of every warp adds the cycles since its previous mark to g_phase[i]; read with glg_debug_phases().
+#ifdef GLG_PHASE_CLOCKS
+static __device__ unsigned long long g_phase[32];   // one copy per translation unit; only glg_race.cu uses it
+static __device__ unsigned long long g_trace[8192 * 4];   // per CTA (last launch wins): start, after wait, end [ns], SM id
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+#define GLG_TRACE(slot) do { if (threadIdx.x == 0 && blockIdx.x < 8192) glg::g_trace[blockIdx.x * 4 + (slot)] = ((slot) == 3) ? (unsigned long long)glg::smid() : glg::globaltimer_ns(); } while (0)
+#define GLG_MARK(i)                                                                  \
+    do {                                                                             \
+        const long long now_ = clock64();                                            \
+        if ((threadIdx.x & 31) == 0) atomicAdd(&glg::g_phase[i], (unsigned long long)(now_ - mark_)); \
+        mark_ = now_;                                                                \
+    } while (0)
+#define GLG_MARK_INIT long long mark_ = clock64()
+#else
+#define GLG_MARK(i) do {} while (0)
+#define GLG_MARK_INIT do {} while (0)
+#define GLG_TRACE(slot) do {} while (0)
+#endif
+
 constexpr unsigned FULL = 0xffffffffu;
 constexpr float INF = __builtin_huge_valf();
 

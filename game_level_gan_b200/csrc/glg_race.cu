@@ -11,6 +11,8 @@
 // kinematics, progress arg-min, wall/finish collision, reward/score, and the ray-cast sensors for
 // its car with the lanes striding over points / walls, and packs the [P,B,O+2] observation.
 // There is no cross-car dependence in the reference step, so no global sync.
+#include <stdlib.h>
+
 #include "glg_common.cuh"
 #include "glg_exact.cuh"
 #include "glg_sensors.cuh"
@@ -31,7 +33,10 @@ struct StepArgs {
     float* rewards_out;
     int32_t* alive_stamp;
     float* history;
+    int32_t* chain;       // [B,P] per-car launch stamps (glg_race_rollout), or nullptr
     int32_t B, N, step_no, record_id;
+    int32_t seq;          // launch sequence number (unique, increasing per environment)
+    int32_t chained;      // wait for chain[car] == seq-1 instead of for the whole previous grid
 };
 
 __global__ void race_init_kernel(glg_race_state st, int K, int32_t* alive_stamp)
@@ -79,6 +84,9 @@ __global__ void __launch_bounds__(32 * GLG_MAX_PLAYERS, GLG_STEP_MINBLOCKS)
 race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    GLG_MARK_INIT;
+    GLG_TRACE(0);
+    GLG_TRACE(3);
     const int N = a.N, B = a.B;
     const int P = pr.num_players;
     const int O = OC ? OC : pr.num_rays;
@@ -102,12 +110,31 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
     // overlap the tail of the previous kernel in the stream; everything below reads what that kernel
     // (the previous step, or the policy that produced the actions) wrote and must wait for it.
     asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int k = b * P + p;
+    if (a.chained) {
+        // Rollout with pre-computed actions: this car's previous step is the only thing the warp depends on
+        // (glg_race_rollout).  The previous launch of the stream is that step's kernel and all of its CTAs have
+        // started (the condition under which a programmatic dependent grid is launched), so the wait is bounded.
+        if (lane == 0) {
+            const int want = a.seq - 1;
+            int got;
+            int spin = 0;
+            do {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(a.chain + k) : "memory");
+                if (++spin > (1 << 24)) __trap();
+            } while (got != want);
+        }
+        __syncwarp();
+    } else {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
+    GLG_MARK(0);
+    GLG_TRACE(1);
 
     // ---- car state and kinematics while the copy is in flight (uniform across the warp) ----
-    const int k = b * P + p;
-    bool alive = a.st.alive[k] != 0;
-    bool fin = a.st.finishes[k] != 0;
+    // (state is read past L1: in a chained rollout the previous step may have run on another SM)
+    bool alive = __ldcg(&a.st.alive[k]) != 0;
+    bool fin = __ldcg(&a.st.finishes[k]) != 0;
     const bool ok = a.valid[b] != 0;
     float2 ext = make_float2(0.f, 0.f);
     if (VARIANT == GLG_STEP_FAST) ext = __ldg(reinterpret_cast<const float2*>(a.extent) + b);
@@ -115,19 +142,21 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
     act = min(max(act, 0), 8);
     if (!alive || !ok) act = 0;                                           // race.py:359
     const int fs = c_steer_idx[act], ft = c_throttle_idx[act];
-    const float2 dir = reinterpret_cast<const float2*>(a.st.directions)[k];
-    const float2 pos = reinterpret_cast<const float2*>(a.st.positions)[k];
+    const float2 dir = __ldcg(reinterpret_cast<const float2*>(a.st.directions) + k);
+    const float2 pos = __ldcg(reinterpret_cast<const float2*>(a.st.positions) + k);
     const float c = pr.turn_cos[p][fs], s = pr.turn_sin[p][fs];
     const P2 nd{xadd(xmul(dir.x, c), xmul(dir.y, s)),                      // race.py:362-364
                 xadd(xmul(dir.x, -s), xmul(dir.y, c))};
-    const float v = xadd(a.st.speeds[k], pr.speed_inc[p][ft]);             // race.py:367
+    const float v = xadd(__ldcg(&a.st.speeds[k]), pr.speed_inc[p][ft]);    // race.py:367
     float nv = fminf(pr.vmax[p], fmaxf(v, 0.f));                           // race.py:369
     const bool moving = fabsf(nv) > 1e-7f;                                 // race.py:370
     const P2 op{pos.x, pos.y};
     const P2 np{xadd(pos.x, xmul(nd.x, nv)), xadd(pos.y, xmul(nd.y, nv))}; // race.py:372
 
+    GLG_MARK(1);
     __syncthreads();                     // barrier init / plain loads visible to every warp
     if (bulk) record_copy_wait(bar);
+    GLG_MARK(2);
     const TrackView tv{pts, pts + 2 * N, N};
     SensorScratch* scratch = reinterpret_cast<SensorScratch*>(smem_raw + smem_scratch_offset(N)) + p;
     unsigned* maskbuf = reinterpret_cast<unsigned*>(smem_raw + smem_maskbuf_offset(N, P)) + (size_t)p * maskbuf_len(N);
@@ -174,6 +203,7 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
         }
         idx = (int)__reduce_min_sync(FULL, (unsigned)first);
     }
+    GLG_MARK(3);
 
     // ---- collisions (race.py:380-447) and sensor candidates in one pass over the polyline ----
     float reward = fin ? 0.f : pr.step_penalty;                            // race.py:382-383
@@ -202,12 +232,13 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
         alive = alive && !dead && !done;                                   // race.py:414, 435
         fin = fin || done;                                                 // race.py:436
         if (lane == 0 && (dead || done)) {
-            int sc = a.st.scores[k];
+            int sc = __ldcg(&a.st.scores[k]);
             if (dead) sc = idx + pr.steps_limit + 1;                       // race.py:442-444
             if (done) sc = a.step_no;                                      // race.py:446-447
             a.st.scores[k] = sc;
         }
     }
+    GLG_MARK(9);
     if (!alive) nv = 0.f;                                                  // race.py:449
     const float drag = xsub(1.f, xmul(xsub(1.f, ft != 0 ? 1.f : 0.f), pr.drag));   // race.py:452
     const float speed = xmul(nv, drag);                                    // race.py:455
@@ -218,7 +249,7 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
         a.st.alive[k] = alive ? 1 : 0;
         a.st.finishes[k] = fin ? 1 : 0;
         a.rewards_out[(size_t)p * B + b] = reward;
-        if (alive && a.alive_stamp) a.alive_stamp[b % GLG_ALIVE_SLOTS] = a.step_no;
+        if (alive && a.alive_stamp) atomicMax(&a.alive_stamp[b % GLG_ALIVE_SLOTS], a.seq);   // launches may overlap
         if (a.history && b == a.record_id) {                               // race.py:492-494
             float* h = a.history + ((size_t)a.step_no * P + p) * 6;
             h[0] = np.x; h[1] = np.y; h[2] = nd.x; h[3] = nd.y; h[4] = (float)act; h[5] = alive ? 1.f : 0.f;
@@ -234,6 +265,7 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
         num = (t != t) ? t : fminf(t, pr.max_distance);                    // NaN propagates like torch.clamp
         den = pr.max_distance;
     }
+    GLG_MARK(11);
     float* out = a.states_out + ((size_t)p * B + b) * (O + 2);
     if (lane == O) { num = speed; den = pr.vmax[p]; }
     if (lane == O + 1) { num = (float)idx; den = pr.progress_div; }
@@ -243,6 +275,15 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
         if (O == 32) out[O] = xdiv(speed, pr.vmax[p]);
         out[O + 1] = xdiv((float)idx, pr.progress_div);
     }
+    if (a.chain) {                       // publish "this car's step `seq` is complete" (all lanes' stores first)
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(a.chain + k), "r"(a.seq) : "memory");
+        }
+    }
+    GLG_MARK(12);
+    GLG_TRACE(2);
 }
 
 __global__ void race_winners_kernel(const int32_t* __restrict__ scores, const uint8_t* __restrict__ finishes,
@@ -300,6 +341,8 @@ static void launch_one(const glg_race_params* pr, const StepArgs& a, cudaStream_
     cfg.gridDim = dim3(a.B);
     cfg.blockDim = dim3(32 * pr->num_players);
     cfg.dynamicSmemBytes = smem_total(a.N, pr->num_players);
+    static const int pad = getenv("GLG_SMEM_PAD") ? atoi(getenv("GLG_SMEM_PAD")) : 0;   // occupancy experiments
+    cfg.dynamicSmemBytes += pad;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see griddepcontrol in the kernel
@@ -323,6 +366,22 @@ static int launch_step(const glg_race_params* pr, const StepArgs& a, int variant
 
 }  // namespace glg
 
+#ifdef GLG_PHASE_CLOCKS
+extern "C" int glg_debug_phases(unsigned long long* out32, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out32, glg::g_phase, sizeof(unsigned long long) * 32);
+    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(glg::g_phase, z, sizeof(z)); }
+    return 0;
+}
+extern "C" int glg_debug_trace(unsigned long long* out, int n)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, glg::g_trace, sizeof(unsigned long long) * n);
+    return 0;
+}
+#endif
+
 extern "C" int glg_race_init(glg_race_state st, int32_t B, int32_t P, int32_t* alive_stamp, glg_stream_t stream)
 {
     using namespace glg;
@@ -338,13 +397,14 @@ extern "C" int glg_race_init(glg_race_state st, int32_t B, int32_t P, int32_t* a
 extern "C" int glg_race_step(const glg_race_params* params, const float* geom, int32_t B, int32_t N,
                              const int64_t* actions, const uint8_t* valid, const float* extent, glg_race_state state,
                              int32_t step_no, float* states_out, float* rewards_out,
-                             int32_t* alive_stamp, float* history, int32_t record_id,
+                             int32_t* alive_stamp, int32_t launch_seq, float* history, int32_t record_id,
                              int32_t variant, glg_stream_t stream)
 {
     using namespace glg;
     const int rc = check_step_args(params, geom, B, N, actions, valid, extent, variant, state, states_out, rewards_out);
     if (rc != GLG_OK || B == 0) return rc;
-    StepArgs a{geom, actions, valid, extent, state, states_out, rewards_out, alive_stamp, history, B, N, step_no, record_id};
+    StepArgs a{geom, actions, valid, extent, state, states_out, rewards_out, alive_stamp, history, nullptr,
+               B, N, step_no, record_id, launch_seq, 0};
     launch_step(params, a, variant, (cudaStream_t)stream);
     return launch_status("glg_race_step");
 }
@@ -353,7 +413,8 @@ extern "C" int glg_race_rollout(const glg_race_params* params, const float* geom
                                 const int64_t* actions, int32_t T, const uint8_t* valid, const float* extent,
                                 glg_race_state state,
                                 int32_t first_step_no, float* states_out, float* rewards_out, int32_t keep_all,
-                                int32_t* alive_stamp, int32_t variant, glg_stream_t stream)
+                                int32_t* alive_stamp, int32_t first_launch_seq, int32_t* chain,
+                                int32_t variant, glg_stream_t stream)
 {
     using namespace glg;
     const int rc = check_step_args(params, geom, B, N, actions, valid, extent, variant, state, states_out, rewards_out);
@@ -364,7 +425,8 @@ extern "C" int glg_race_rollout(const glg_race_params* params, const float* geom
         StepArgs a{geom, actions + (size_t)t * PB, valid, extent, state,
                    keep_all ? states_out + (size_t)t * PB * W : states_out,
                    keep_all ? rewards_out + (size_t)t * PB : rewards_out,
-                   alive_stamp, nullptr, B, N, first_step_no + t, -1};
+                   alive_stamp, nullptr, chain, B, N, first_step_no + t, -1, first_launch_seq + t,
+                   (chain != nullptr && t > 0) ? 1 : 0};
         launch_step(params, a, variant, (cudaStream_t)stream);
     }
     return launch_status("glg_race_rollout");

@@ -395,6 +395,7 @@ __device__ __forceinline__ ScanResult scan_two_stage(const TrackView& tv, const 
     if (lane == 0) sc->nan_mask = 0;
 
     // ---- stage 1 ----
+    GLG_MARK_INIT;
     // Lmax excludes the start line (wall N-1, as long as the track is wide): it is appended to both lists below.
     const float Rc = fmaf(RC_FACTOR, Lmax, 1e-3f);
     const float close2 = Rc * Rc * d2 * 1.0001f;                       // thresholds on |z|^2 = r^2 d2
@@ -422,6 +423,7 @@ __device__ __forceinline__ ScanResult scan_two_stage(const TrackView& tv, const 
         if (fabsf(im9) <= Kn * (r4 * r4) || r2z <= close2) fbits |= bit;
         if (r2z <= col2) cbits |= bit;
     }
+    GLG_MARK(5);
     // wall w = (vertex w, vertex w+1): the next vertex lives in lane+1 (same pass), or in lane 0 of the next pass
     unsigned s1 = __shfl_down_sync(FULL, sbits, 1), f1 = __shfl_down_sync(FULL, fbits, 1);
     const unsigned s0 = __shfl_sync(FULL, sbits, 0), f0 = __shfl_sync(FULL, fbits, 0);
@@ -466,6 +468,7 @@ __device__ __forceinline__ ScanResult scan_two_stage(const TrackView& tv, const 
         ++nc;
     }
     __syncwarp();
+    GLG_MARK(6);
 
     // ---- collision: exact test of the walls near the path (race.py:406) ----
     if (nc) {
@@ -486,6 +489,7 @@ __device__ __forceinline__ ScanResult scan_two_stage(const TrackView& tv, const 
         res.wall_hit = __any_sync(FULL, hit);
     }
 
+    GLG_MARK(7);
     // ---- stage 2: candidate rays of the flagged walls ----
     const float sect = (float)O * (0.5f / PI_F);
     const float m_eta = ETA_ANGLE * sect, m_eps = EPS_PERP * sect, fhalf = 0.5f * (float)O;
@@ -515,6 +519,7 @@ __device__ __forceinline__ ScanResult scan_two_stage(const TrackView& tv, const 
         }
         if (overflow) break;
     }
+    GLG_MARK(8);
     res.safe = !overflow;
     res.queued = total;
     return res;
@@ -525,7 +530,9 @@ __device__ __forceinline__ float sensors_finish(const TrackView& tv, const glg_r
                                                 SensorScratch* sc, const ScanResult& res, int O)
 {
     if (!res.safe) return sensors_brute(tv, pr, s, nd);
+    GLG_MARK_INIT;
     queue_flush(tv, s, sc, res.queued);
+    GLG_MARK(10);
     const int lane = lane_id();
     float t = INF;
     if (lane < O) {

@@ -166,6 +166,8 @@ class Race(MultiEnvironment):
             self.scores = torch.empty((B, P), dtype=torch.int32, device=dev)
             self._stamp = torch.empty((_lib.ALIVE_SLOTS,), dtype=torch.int32, device=dev)
             self._stamp_host = torch.zeros((_lib.ALIVE_SLOTS,), dtype=torch.int32).pin_memory()
+            self._chain = torch.zeros((B, P), dtype=torch.int32, device=dev)      # per-car launch stamps (rollout)
+            self._seq = 0                                                         # launch sequence number
             self._state = RaceState(ptr(self.positions), ptr(self.directions), ptr(self.speeds),
                                     ptr(self._alive), ptr(self._finishes), ptr(self.scores))
             check(lib.glg_race_init(self._state, B, P, ptr(self._stamp), stream), 'glg_race_init')
@@ -202,17 +204,20 @@ class Race(MultiEnvironment):
                     self._hist = grown
                 hist = self._hist
                 self._hist_steps.append(self.steps)
+            self._seq += 1
             check(_lib.lib().glg_race_step(
                 self._params, ptr(self._geom), B, self._geom.size(2), ptr(actions), ptr(self._valid_tracks),
-                ptr(self._extent), self._state, self.steps, ptr(states), ptr(rewards), ptr(self._stamp), ptr(hist),
-                self.record_id, self._variant_code(), _lib.stream_ptr(dev)), 'glg_race_step')
+                ptr(self._extent), self._state, self.steps, ptr(states), ptr(rewards), ptr(self._stamp), self._seq,
+                ptr(hist), self.record_id, self._variant_code(), _lib.stream_ptr(dev)), 'glg_race_step')
             self._alive_known = None
             return states, rewards
 
-    def rollout(self, actions, keep_all=False):
+    def rollout(self, actions, keep_all=False, chained=True):
         """T steps with pre-computed actions [T,P,B] (no per-step host work).  Returns the outputs of
         the last step, or of all steps ([T,P,B,O+2], [T,P,B]) with keep_all.  Equivalent to T calls of
-        `step` as long as somebody is alive throughout (the 19-wide early-out is not applied)."""
+        `step` as long as somebody is alive throughout (the 19-wide early-out is not applied).
+        `chained`: consecutive step kernels depend on each other car by car instead of grid by grid, so
+        they overlap (include/glg_b200.h, glg_race_rollout); the results are the same."""
         dev = self.device
         with torch.no_grad():
             actions = actions.detach().to(device=dev, dtype=torch.int64).contiguous()
@@ -225,7 +230,9 @@ class Race(MultiEnvironment):
             check(_lib.lib().glg_race_rollout(
                 self._params, ptr(self._geom), B, self._geom.size(2), ptr(actions), T, ptr(self._valid_tracks),
                 ptr(self._extent), self._state, self.steps + 1, ptr(states), ptr(rewards), int(keep_all), ptr(self._stamp),
+                self._seq + 1, ptr(self._chain) if chained else None,
                 self._variant_code(), _lib.stream_ptr(dev)), 'glg_race_rollout')
+            self._seq += T
             self.steps += T
             self._alive_known = None
             return states, rewards
@@ -234,7 +241,7 @@ class Race(MultiEnvironment):
         """Copy of the mutable episode state (the reference has no env checkpoint; used to rewind
         rollouts, e.g. by bench.py).  Geometry and validity are not part of it."""
         live = (self.positions, self.directions, self.speeds, self._alive, self._finishes, self.scores)
-        return {'tensors': tuple(x.clone() for x in live), 'steps': self.steps,
+        return {'tensors': tuple(x.clone() for x in live), 'steps': self.steps,   # _seq is never rewound
                 'alive_known': self._any_alive()}
 
     def restore(self, snap):
@@ -249,7 +256,7 @@ class Race(MultiEnvironment):
         if self._alive_known is None:
             self._stamp_host.copy_(self._stamp, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
-            self._alive_known = bool((self._stamp_host == self.steps).any())
+            self._alive_known = bool((self._stamp_host == self._seq).any())
         return self._alive_known
 
     def finished(self):

@@ -121,24 +121,31 @@ int glg_race_init(glg_race_state state, int32_t B, int32_t P, int32_t* alive_sta
  *   extent     [B,2] f32 from glg_track_extent (required by GLG_STEP_FAST, else may be NULL)
  *   step_no    value of Race.steps AFTER the increment of this step (race.py:349)
  *   states_out [P,B,num_rays+2] f32, rewards_out [P,B] f32
- *   alive_stamp [GLG_ALIVE_SLOTS] i32 or NULL: slot (b % 64) := step_no if track b still has an
- *              alive car after this step (host reads it for Race.finished(), race.py:502-504)
+ *   alive_stamp [GLG_ALIVE_SLOTS] i32 or NULL: slot (b % 64) := max(slot, launch_seq) if track b still
+ *              has an alive car after this step (host reads it for Race.finished(), race.py:502-504)
+ *   launch_seq a number the caller increases with every launch on this environment (> 0)
  *   history    optional [>= step_no+1, P, 6] f32 ring written for track `record_id`
  *              (x, y, dx, dy, masked action, alive) at row step_no (race.py:492-494), or NULL
  *   variant    GLG_STEP_FAST, GLG_STEP_SCAN or GLG_STEP_BRUTE (identical results)                */
 int glg_race_step(const glg_race_params* params, const float* geom, int32_t B, int32_t N,
                   const int64_t* actions, const uint8_t* valid, const float* extent, glg_race_state state,
                   int32_t step_no, float* states_out, float* rewards_out,
-                  int32_t* alive_stamp, float* history, int32_t record_id,
+                  int32_t* alive_stamp, int32_t launch_seq, float* history, int32_t record_id,
                   int32_t variant, glg_stream_t stream);
 
 /* T consecutive steps with pre-computed actions [T,P,B] (random-action rollouts, replay).
  * Launches T step kernels back to back on `stream`; states_out/rewards_out hold the LAST step's
- * outputs, or all steps if `keep_all` (then [T,P,B,W] / [T,P,B]).  first_step_no as in glg_race_step. */
+ * outputs, or all steps if `keep_all` (then [T,P,B,W] / [T,P,B]).  first_step_no as in glg_race_step;
+ * launch t uses launch_seq = first_launch_seq + t.
+ *   chain  [B,P] i32 scratch or NULL.  With it, launches 1..T-1 do not wait for the whole previous grid but,
+ *          warp by warp, for the previous step of their own car (chain[car] == launch_seq - 1, published with
+ *          release/acquire), so consecutive steps overlap; results are identical.  The numbers
+ *          first_launch_seq .. first_launch_seq+T-1 must be larger than anything stored in `chain` before. */
 int glg_race_rollout(const glg_race_params* params, const float* geom, int32_t B, int32_t N,
                      const int64_t* actions, int32_t T, const uint8_t* valid, const float* extent,
                      glg_race_state state, int32_t first_step_no, float* states_out, float* rewards_out, int32_t keep_all,
-                     int32_t* alive_stamp, int32_t variant, glg_stream_t stream);
+                     int32_t* alive_stamp, int32_t first_launch_seq, int32_t* chain,
+                     int32_t variant, glg_stream_t stream);
 
 /* Winner per track.  Replaces Race.winners, games/race.py:506-529.  winners [B] i64 out.      */
 int glg_race_winners(const int32_t* scores, const uint8_t* finishes, const uint8_t* valid,

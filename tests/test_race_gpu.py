@@ -156,14 +156,25 @@ def test_rollout_equals_steps_and_winner_stats():
     B = trials * boards
     acts = torch.randint(0, 9, (T, 2, B), generator=g)
     a = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
-    b = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
     a.reset(tracks)
-    b.reset(tracks)
     per_step = [a.step(acts[s].cuda()) for s in range(T)]
-    states, rewards = b.rollout(acts.cuda(), keep_all=True)
-    assert eq(states, torch.stack([s for s, _ in per_step])) and eq(rewards, torch.stack([r for _, r in per_step]))
-    assert eq(a.positions, b.positions) and eq(a.scores, b.scores) and a.steps == b.steps
-    assert a.finished() == b.finished()
+    for chained in (True, False):
+        b = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
+        b.reset(tracks)
+        states, rewards = b.rollout(acts.cuda(), keep_all=True, chained=chained)
+        assert eq(states, torch.stack([s for s, _ in per_step])) and eq(rewards, torch.stack([r for _, r in per_step]))
+        assert eq(a.positions, b.positions) and eq(a.scores, b.scores) and a.steps == b.steps
+        assert a.finished() == b.finished()
+        # rewind and replay in two chained pieces, keeping only the last outputs (same buffer every step)
+        c = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
+        c.reset(tracks)
+        snap = c.snapshot()
+        c.rollout(acts[:17].cuda(), chained=chained)
+        c.restore(snap)
+        c.rollout(acts[:30].cuda(), chained=chained)
+        s_last, r_last = c.rollout(acts[30:].cuda(), chained=chained)
+        assert eq(s_last, per_step[-1][0]) and eq(r_last, per_step[-1][1]) and eq(c.positions, a.positions)
+        assert c.finished() == a.finished()
     w = a.winners()
     ref = torch.nn.functional.one_hot(w.cpu() + 1, 3).view(trials, -1, 3).float().mean(0)
     assert eq(a.winner_stats(trials), ref)
