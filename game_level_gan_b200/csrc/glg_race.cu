@@ -190,10 +190,19 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
         const float smin = __fsqrt_rn(qmin);
         const float qcut = qmin * 1.000001f + 1e-45f;
         int first = 0x7fffffff;
+        // almost always a single (u, lane) is within qcut; the correctly rounded sqrt is taken only there
+        unsigned cand = 0;
 #pragma unroll
-        for (int u = KEEP - 1; u >= 0; --u)
-            if (qk[u] <= qcut && __fsqrt_rn(qk[u]) == smin) first = lane + 32 * u;
-        if (first == 0x7fffffff) {
+        for (int u = 0; u < KEEP; ++u) cand |= (qk[u] <= qcut) ? (1u << u) : 0u;
+        while (cand) {
+            const int u = __ffs(cand) - 1;
+            cand &= cand - 1;
+            float q = qk[0];
+#pragma unroll
+            for (int w = 1; w < KEEP; ++w) q = (u == w) ? qk[w] : q;
+            if (__fsqrt_rn(q) == smin) { first = lane + 32 * u; break; }
+        }
+        if (__all_sync(FULL, first == 0x7fffffff)) {
             for (int j = lane + 32 * KEEP; j < N; j += 32) {
                 const float2 cpt = tv.centre[j];
                 const float ex = xsub(np.x, cpt.x), ey = xsub(np.y, cpt.y);

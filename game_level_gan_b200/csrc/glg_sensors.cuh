@@ -400,15 +400,17 @@ __device__ __forceinline__ ScanResult scan_two_stage(const TrackView& tv, const 
     const float Rc = fmaf(RC_FACTOR, Lmax, 1e-3f);
     const float close2 = Rc * Rc * d2 * 1.0001f;                       // thresholds on |z|^2 = r^2 d2
     const float colR = fabsf(op.x - s.x) + fabsf(op.y - s.y) + Lmax + 1e-3f;
-    const float col2 = need_col ? colR * colR * d2 * 1.0001f : -1.f;
+    const float col2 = need_col ? colR * colR * d2 * 1.0001f : 0.f;    // r2z - col2 < 0 never holds for 0
     const float Kn = 9.f * EPS_PERP * 1.4143f * 1.001f;                // 9 EPS_PERP |nd| with |nd| < sqrt(2)
     const int passes = (V + 31) / 32;                                  // <= 32 (N <= 512)
-    // lane l handles vertices l, l+32, ...; bit `pass` of sbits / fbits / cbits describes vertex 32*pass + l
+    // lane l handles vertices l, l+32, ...; bit `pass` of sbits / fbits / cbits describes vertex 32*pass + l.
+    // The three predicates are produced as SIGN BITS (x < 0) and shifted in with one funnel shift each; the
+    // bits arrive in reverse pass order and are put right after the loop.  Vertices past the polyline (the
+    // last pass may read up to 31 points of whatever follows `line` in shared memory) are masked by `own`.
     unsigned sbits = 0, fbits = 0, cbits = 0;
 #pragma unroll 3
     for (int pass = 0; pass < passes; ++pass) {
-        const int v = pass * 32 + lane;
-        const float2 pt = tv.line[min(v, V - 1)];
+        const float2 pt = tv.line[pass * 32 + lane];
         const float ux = pt.x - s.x, uy = pt.y - s.y;
         const float a = fmaf(ux, nd.x, uy * nd.y);
         const float b = fmaf(ux, nd.y, -(uy * nd.x));
@@ -418,10 +420,17 @@ __device__ __forceinline__ ScanResult scan_two_stage(const TrackView& tv, const 
         const float im3 = b * fmaf(3.f, a2, -b2);
         const float im9 = im3 * fmaf(3.f, re3 * re3, -(im3 * im3));    // Im (z^3)^3
         const float r4 = r2z * r2z;
-        const unsigned bit = 1u << pass;
-        if (im9 < 0.f) sbits |= bit;
-        if (fabsf(im9) <= Kn * (r4 * r4) || r2z <= close2) fbits |= bit;
-        if (r2z <= col2) cbits |= bit;
+        const float near = fmaf(r4 * r4, -Kn, fabsf(im9));             // < 0: within EPS_PERP of a ray line
+        const float flag = fminf(near, r2z - close2);                  // < 0: near a ray line or close to the car
+        sbits = __funnelshift_l(__float_as_uint(im9), sbits, 1);
+        fbits = __funnelshift_l(__float_as_uint(flag), fbits, 1);
+        cbits = __funnelshift_l(__float_as_uint(r2z - col2), cbits, 1);
+    }
+    {
+        const int sh = 32 - passes;
+        sbits = __brev(sbits) >> sh;
+        fbits = __brev(fbits) >> sh;
+        cbits = __brev(cbits) >> sh;
     }
     GLG_MARK(5);
     // wall w = (vertex w, vertex w+1): the next vertex lives in lane+1 (same pass), or in lane 0 of the next pass
