@@ -38,6 +38,7 @@ import torch  # noqa: E402
 B_TRACKS, P_CARS, L_SEG, O_RAYS = 4096, 2, 128, 18
 REPLICAS = 16   # default of --replicas
 CYCLE = 100
+KEEP_ALL = True      # every step's observations and rewards are kept ([CYCLE,P,B,20] per cycle), not only the last
 PREROLL = 100
 SEED = 1234
 ALGO_BYTES_PER_TRACK = 3 * (L_SEG + 2) * 8        # centre + left + right points, SURVEY.md 8(d)
@@ -217,7 +218,7 @@ class Replica(object):
 
     def cycle(self, n):
         self.restore()
-        self.env.rollout(self.acts[PREROLL:PREROLL + n])
+        self.env.rollout(self.acts[PREROLL:PREROLL + n], keep_all=KEEP_ALL)
 
 
 def run_b200(args, rank, world):

@@ -139,7 +139,9 @@ int glg_race_step(const glg_race_params* params, const float* geom, int32_t B, i
  * launch t uses launch_seq = first_launch_seq + t.
  *   chain  [B,P] i32 scratch or NULL.  With it, launches 1..T-1 do not wait for the whole previous grid but,
  *          warp by warp, for the previous step of their own car (chain[car] == launch_seq - 1, published with
- *          release/acquire), so consecutive steps overlap; results are identical.  The numbers
+ *          release/acquire), so consecutive steps overlap; results are identical.  With keep_all the stamp is
+ *          published right after the car state is written back (before the ray cast), without it after the
+ *          outputs (the steps share one output buffer).  The numbers
  *          first_launch_seq .. first_launch_seq+T-1 must be larger than anything stored in `chain` before. */
 int glg_race_rollout(const glg_race_params* params, const float* geom, int32_t B, int32_t N,
                      const int64_t* actions, int32_t T, const uint8_t* valid, const float* extent,
