@@ -13,7 +13,7 @@ MAX_PLAYERS = 8
 MAX_RAYS = 32
 ALIVE_SLOTS = 64
 STEP_FAST, STEP_BRUTE, STEP_SCAN = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class GlgError(RuntimeError):
@@ -50,7 +50,7 @@ SYMBOLS = {
     'glg_track_extent': (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp]),
     'glg_race_init': (ctypes.c_int, [RaceState, _i32, _i32, _vp, _vp]),
     'glg_race_step': (ctypes.c_int, [ctypes.POINTER(RaceParams), _vp, _i32, _i32, _vp, _vp, _vp, RaceState,
-                                     _i32, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _vp]),
+                                     _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp]),
     'glg_race_rollout': (ctypes.c_int, [ctypes.POINTER(RaceParams), _vp, _i32, _i32, _vp, _i32, _vp, _vp,
                                         RaceState, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _vp]),
     'glg_race_winners': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),

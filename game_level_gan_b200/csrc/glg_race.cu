@@ -32,6 +32,7 @@ struct StepArgs {
     int32_t* alive_stamp;
     float* history;
     int32_t* chain;       // [B,P] per-car launch stamps (glg_race_rollout), or nullptr
+    const int32_t* base;  // device {step_no offset, launch_seq offset} (CUDA-graph replays), or nullptr
     int32_t B, N, step_no, record_id;
     int32_t seq;          // launch sequence number (unique, increasing per environment)
     int32_t chained;      // wait for chain[car] == seq-1 instead of for the whole previous grid
@@ -84,6 +85,14 @@ __global__ void __launch_bounds__(32 * GLG_MAX_PLAYERS, GLG_STEP_MINBLOCKS)
 race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    // every kernel parameter is baked into a captured graph: replays take the running step number from memory
+    int step_no = a.step_no, seq = a.seq;
+    if (a.base) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        step_no += __ldcg(a.base);
+        seq += __ldcg(a.base + 1);
+        if (step_no > pr.steps_limit + 1) return;     // past the time limit (Race.finished()): the step is a no-op
+    }
     GLG_MARK_INIT;
     GLG_TRACE(0);
     GLG_TRACE(3);
@@ -116,7 +125,7 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
         // (glg_race_rollout).  The previous launch of the stream is that step's kernel and all of its CTAs have
         // started (the condition under which a programmatic dependent grid is launched), so the wait is bounded.
         if (lane == 0) {
-            const int want = a.seq - 1;
+            const int want = seq - 1;
             int got;
             int spin = 0;
             do {
@@ -243,7 +252,7 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
         if (lane == 0 && (dead || done)) {
             int sc = __ldcg(&a.st.scores[k]);
             if (dead) sc = idx + pr.steps_limit + 1;                       // race.py:442-444
-            if (done) sc = a.step_no;                                      // race.py:446-447
+            if (done) sc = step_no;                                      // race.py:446-447
             a.st.scores[k] = sc;
         }
     }
@@ -258,14 +267,14 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
         a.st.alive[k] = alive ? 1 : 0;
         a.st.finishes[k] = fin ? 1 : 0;
         a.rewards_out[(size_t)p * B + b] = reward;
-        if (alive && a.alive_stamp) atomicMax(&a.alive_stamp[b % GLG_ALIVE_SLOTS], a.seq);   // launches may overlap
+        if (alive && a.alive_stamp) atomicMax(&a.alive_stamp[b % GLG_ALIVE_SLOTS], seq);   // launches may overlap
         if (a.history && b == a.record_id) {                               // race.py:492-494
-            float* h = a.history + ((size_t)a.step_no * P + p) * 6;
+            float* h = a.history + ((size_t)step_no * P + p) * 6;
             h[0] = np.x; h[1] = np.y; h[2] = nd.x; h[3] = nd.y; h[4] = (float)act; h[5] = alive ? 1.f : 0.f;
         }
         // the next step of this car needs nothing else from this one: let it start while the rays are cast
         if (a.chain && a.early)
-            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(a.chain + k), "r"(a.seq) : "memory");
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(a.chain + k), "r"(seq) : "memory");
     }
 
     // ---- sensors (race.py:459-489) and observation pack [P,B,O+2] (race.py:496-500) ----
@@ -291,7 +300,7 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
         __syncwarp();
         if (lane == 0) {
             __threadfence();
-            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(a.chain + k), "r"(a.seq) : "memory");
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(a.chain + k), "r"(seq) : "memory");
         }
     }
     GLG_MARK(12);
@@ -359,8 +368,10 @@ static void launch_one(const glg_race_params* pr, const StepArgs& a, cudaStream_
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see griddepcontrol in the kernel
     attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cap);
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = cap == cudaStreamCaptureStatusNone ? 1 : 0;         // plain stream order inside a captured graph
     cudaLaunchKernelEx(&cfg, race_step_kernel<VARIANT, OC>, *pr, a);
 }
 
@@ -409,13 +420,13 @@ extern "C" int glg_race_init(glg_race_state st, int32_t B, int32_t P, int32_t* a
 extern "C" int glg_race_step(const glg_race_params* params, const float* geom, int32_t B, int32_t N,
                              const int64_t* actions, const uint8_t* valid, const float* extent, glg_race_state state,
                              int32_t step_no, float* states_out, float* rewards_out,
-                             int32_t* alive_stamp, int32_t launch_seq, float* history, int32_t record_id,
-                             int32_t variant, glg_stream_t stream)
+                             int32_t* alive_stamp, int32_t launch_seq, const int32_t* base, float* history,
+                             int32_t record_id, int32_t variant, glg_stream_t stream)
 {
     using namespace glg;
     const int rc = check_step_args(params, geom, B, N, actions, valid, extent, variant, state, states_out, rewards_out);
     if (rc != GLG_OK || B == 0) return rc;
-    StepArgs a{geom, actions, valid, extent, state, states_out, rewards_out, alive_stamp, history, nullptr,
+    StepArgs a{geom, actions, valid, extent, state, states_out, rewards_out, alive_stamp, history, nullptr, base,
                B, N, step_no, record_id, launch_seq, 0, 0};
     launch_step(params, a, variant, (cudaStream_t)stream);
     return launch_status("glg_race_step");
@@ -437,7 +448,7 @@ extern "C" int glg_race_rollout(const glg_race_params* params, const float* geom
         StepArgs a{geom, actions + (size_t)t * PB, valid, extent, state,
                    keep_all ? states_out + (size_t)t * PB * W : states_out,
                    keep_all ? rewards_out + (size_t)t * PB : rewards_out,
-                   alive_stamp, nullptr, chain, B, N, first_step_no + t, -1, first_launch_seq + t,
+                   alive_stamp, nullptr, chain, nullptr, B, N, first_step_no + t, -1, first_launch_seq + t,
                    (chain != nullptr && t > 0) ? 1 : 0, keep_all ? 1 : 0};
         launch_step(params, a, variant, (cudaStream_t)stream);
     }

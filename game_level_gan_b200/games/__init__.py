@@ -5,6 +5,7 @@ from .race import Race, RaceCar
 from .race_utils import RaceConfig, predefined_tracks, race_game
 from .pytorch_wrapper import PytorchWrapper
 from . import game_helpers
+from .rollout import GraphedRollout
 
 __all__ = ['MultiEnvironment', 'Pacman', 'Race', 'RaceCar', 'RaceConfig', 'predefined_tracks', 'race_game',
-           'PytorchWrapper', 'game_helpers']
+           'PytorchWrapper', 'game_helpers', 'GraphedRollout']

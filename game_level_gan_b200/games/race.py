@@ -208,9 +208,19 @@ class Race(MultiEnvironment):
             check(_lib.lib().glg_race_step(
                 self._params, ptr(self._geom), B, self._geom.size(2), ptr(actions), ptr(self._valid_tracks),
                 ptr(self._extent), self._state, self.steps, ptr(states), ptr(rewards), ptr(self._stamp), self._seq,
-                ptr(hist), self.record_id, self._variant_code(), _lib.stream_ptr(dev)), 'glg_race_step')
+                None, ptr(hist), self.record_id, self._variant_code(), _lib.stream_ptr(dev)), 'glg_race_step')
             self._alive_known = None
             return states, rewards
+
+    def step_into(self, actions, states_out, rewards_out, base, offset):
+        """Capture-safe step for CUDA graphs (games/rollout.py): no allocation, no host synchronisation, no
+        early-out; the step number and launch number are `offset` plus the two int32 counters in the
+        device tensor `base`, and steps past the time limit do nothing (include/glg_b200.h)."""
+        B = self.num_tracks
+        check(_lib.lib().glg_race_step(
+            self._params, ptr(self._geom), B, self._geom.size(2), ptr(actions), ptr(self._valid_tracks),
+            ptr(self._extent), self._state, offset, ptr(states_out), ptr(rewards_out), ptr(self._stamp), offset,
+            ptr(base), None, -1, self._variant_code(), _lib.stream_ptr(self.device)), 'glg_race_step')
 
     def rollout(self, actions, keep_all=False, chained=True):
         """T steps with pre-computed actions [T,P,B] (no per-step host work).  Returns the outputs of

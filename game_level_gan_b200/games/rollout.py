@@ -1,0 +1,86 @@
+"""Whole-episode rollouts without per-step host work.
+
+The reference plays an episode with a Python loop that synchronises with the device twice per step
+(train-gan.py:91-93: `while any_valid and not game.finished(): actions = ...act(s)...; game.step(actions)`).
+`GraphedRollout` captures `k` iterations of [policy -> env step] in ONE CUDA graph - the policy stays
+whatever PyTorch code the caller provides (the reference's PPOAgent / LSTMPolicy), the step is the
+sm_100a kernel - replays it, and looks at `finished()` once per replay.  Steps that a replay runs after
+the episode has ended change nothing (dead and finished cars are frozen, steps past the time limit are
+no-ops in the kernel), and `Race.steps` is set to what the reference's loop would have counted, so the
+state of the environment after `run()` is the same as after the reference's loop.
+"""
+import torch
+
+from .._lib import GlgError
+
+
+class GraphedRollout(object):
+    def __init__(self, env, act, steps_per_replay=8, on_reset=None):
+        """env: a reset `Race`; act(states [P,B,O+2]) -> actions [P,B] int64 (capture-safe torch code:
+        no host synchronisation, no data-dependent shapes; recurrent state kept in tensors updated in
+        place).  on_reset(): called after the warm-up pass of `capture` and at the start of `run` (e.g.
+        zero the policies' recurrent state, like PPOAgent.reset, agents/PPOAgent.py:40-44)."""
+        if env.num_tracks is None or env.num_tracks == 0:
+            raise GlgError('GraphedRollout needs a reset environment with at least one track')
+        self.env, self.act, self.k, self.on_reset = env, act, int(steps_per_replay), on_reset
+        dev = env.device
+        B, P, O = env.num_tracks, env.num_players, env.observation_size
+        self.states = torch.zeros((P, B, O + 2), dtype=torch.float32, device=dev)
+        self.rewards = torch.zeros((P, B), dtype=torch.float32, device=dev)
+        self.actions = torch.zeros((P, B), dtype=torch.int64, device=dev)
+        self.base = torch.zeros((2,), dtype=torch.int32, device=dev)      # {step number, launch number} so far
+        self.graph = None
+
+    def _body(self):
+        for j in range(1, self.k + 1):
+            self.actions.copy_(self.act(self.states))
+            self.env.step_into(self.actions, self.states, self.rewards, self.base, j)
+        self.base += self.k
+
+    def capture(self):
+        side = torch.cuda.Stream(device=self.env.device)
+        side.wait_stream(torch.cuda.current_stream(self.env.device))
+        with torch.cuda.stream(side), torch.no_grad():      # warm-up outside the graph (allocator, lazy init)
+            saved = self.env.snapshot(), self.env._chain.clone(), self.env._stamp.clone(), self.states.clone()
+            self.base.copy_(torch.tensor([self.env.steps, self.env._seq], dtype=torch.int32))
+            self._body()
+            side.synchronize()
+            self.env.restore(saved[0])
+            self.env._chain.copy_(saved[1]); self.env._stamp.copy_(saved[2]); self.states.copy_(saved[3])
+            if self.on_reset is not None:
+                self.on_reset()
+            side.synchronize()
+        torch.cuda.current_stream(self.env.device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self._body()
+        return self
+
+    def run(self, states, max_replays=None):
+        """Play the episode from the observation `states` (of `reset` or the last `step`) to its end.
+        Returns (last states, last rewards)."""
+        env = self.env
+        if self.graph is None:
+            self.capture()
+        self.states.copy_(states)
+        if self.on_reset is not None:
+            self.on_reset()
+        start_steps, start_seq = env.steps, env._seq
+        self.base.copy_(torch.tensor([start_steps, start_seq], dtype=torch.int32), non_blocking=True)
+        replays = 0
+        while not env.finished() and (max_replays is None or replays < max_replays):
+            self.graph.replay()
+            replays += 1
+            env.steps += self.k
+            env._seq += self.k
+            env._alive_known = None
+        if replays and env.finished():
+            # the reference's loop stops right after the step that ended the episode
+            env._stamp_host.copy_(env._stamp)
+            torch.cuda.current_stream(env.device).synchronize()
+            last_alive = int(env._stamp_host.max())                # launch number after which somebody was still alive
+            by_death = (max(last_alive, start_seq) - start_seq) + 1 if last_alive >= start_seq else 0
+            by_time = env.steps_limit + 1 - start_steps
+            ran = replays * self.k
+            env.steps = start_steps + min(ran, by_death, by_time)
+        return self.states, self.rewards

@@ -124,14 +124,18 @@ int glg_race_init(glg_race_state state, int32_t B, int32_t P, int32_t* alive_sta
  *   alive_stamp [GLG_ALIVE_SLOTS] i32 or NULL: slot (b % 64) := max(slot, launch_seq) if track b still
  *              has an alive car after this step (host reads it for Race.finished(), race.py:502-504)
  *   launch_seq a number the caller increases with every launch on this environment (> 0)
+ *   base       NULL, or a device pointer to {step_no offset, launch_seq offset} (2 x i32) that the kernel adds to
+ *              step_no / launch_seq: a launch captured in a CUDA graph is replayed with the running numbers
+ *              kept in memory.  With `base`, a step whose number exceeds steps_limit + 1 (the episode timed
+ *              out, race.py:502-504) does nothing, so a graph may run past the end of the episode.
  *   history    optional [>= step_no+1, P, 6] f32 ring written for track `record_id`
  *              (x, y, dx, dy, masked action, alive) at row step_no (race.py:492-494), or NULL
  *   variant    GLG_STEP_FAST, GLG_STEP_SCAN or GLG_STEP_BRUTE (identical results)                */
 int glg_race_step(const glg_race_params* params, const float* geom, int32_t B, int32_t N,
                   const int64_t* actions, const uint8_t* valid, const float* extent, glg_race_state state,
                   int32_t step_no, float* states_out, float* rewards_out,
-                  int32_t* alive_stamp, int32_t launch_seq, float* history, int32_t record_id,
-                  int32_t variant, glg_stream_t stream);
+                  int32_t* alive_stamp, int32_t launch_seq, const int32_t* base, float* history,
+                  int32_t record_id, int32_t variant, glg_stream_t stream);
 
 /* T consecutive steps with pre-computed actions [T,P,B] (random-action rollouts, replay).
  * Launches T step kernels back to back on `stream`; states_out/rewards_out hold the LAST step's

@@ -46,7 +46,7 @@ def test_argument_validation_without_device():
     pr = _lib.RaceParams()
     pr.num_players = 99
     st = _lib.RaceState()
-    assert lib.glg_race_step(ctypes.byref(pr), None, 1, 130, None, None, None, st, 1, None, None, None, 1, None, 0, 0, None) == -1
+    assert lib.glg_race_step(ctypes.byref(pr), None, 1, 130, None, None, None, st, 1, None, None, None, 1, None, None, 0, 0, None) == -1
 
 
 def test_host_tables_match_reference_constants():

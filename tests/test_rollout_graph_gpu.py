@@ -1,0 +1,74 @@
+"""GraphedRollout (one CUDA graph of k x [policy -> env step]) against the reference's per-step loop
+(train-gan.py:91-93) run with the same deterministic policies: the environment must end in the same state."""
+import pytest
+import torch
+
+from tests.helpers import eq
+
+pytestmark = pytest.mark.gpu
+
+
+class RecurrentArgmaxPolicy(object):
+    """LSTMPolicy-like (policies/LSTMPolicy.py:26-41): two LSTM cells + linear head per player, greedy action,
+    recurrent state kept in place so the same code runs eagerly and inside a captured graph."""
+
+    def __init__(self, P, B, width, seed, hidden=32):
+        g = torch.Generator().manual_seed(seed)
+        self.cells = [[torch.nn.LSTMCell(width if i == 0 else hidden, hidden).cuda() for i in range(2)] for _ in range(P)]
+        self.heads = [torch.nn.Linear(hidden, 9).cuda() for _ in range(P)]
+        for mods in self.cells:
+            for m in mods:
+                for w in m.parameters():
+                    w.data.copy_(torch.randn(w.shape, generator=g) * 0.4)
+        for p, m in enumerate(self.heads):
+            for w in m.parameters():
+                w.data.copy_(torch.randn(w.shape, generator=g) * (0.5 if p else 2.0))
+        self.h = [[(torch.zeros(B, hidden, device='cuda'), torch.zeros(B, hidden, device='cuda')) for _ in range(2)] for _ in range(P)]
+
+    def reset(self):
+        for per_player in self.h:
+            for h, c in per_player:
+                h.zero_(); c.zero_()
+
+    def __call__(self, states):
+        acts = []
+        for p in range(len(self.cells)):
+            x = states[p]
+            for i, cell in enumerate(self.cells[p]):
+                h, c = cell(x, self.h[p][i])
+                self.h[p][i][0].copy_(h); self.h[p][i][1].copy_(c)
+                x = h
+            logits = self.heads[p](x)
+            logits[:, 1] += 1.5                      # bias towards "forward" so that cars travel
+            acts.append(torch.argmax(logits, dim=-1))
+        return torch.stack(acts, 0)
+
+
+@pytest.mark.parametrize('timeout,k', [(3., 7), (40., 16)])
+def test_graphed_rollout_matches_the_reference_loop(timeout, k):
+    from game_level_gan_b200.games import GraphedRollout, Race, RaceConfig
+    g = torch.Generator().manual_seed(31)
+    B = 96
+    tracks = torch.zeros(B, 128, 2)
+    tracks[:, :, 0] = torch.linspace(-1., 1., 9)[torch.randint(0, 9, (B, 128), generator=g)]
+    with torch.no_grad():
+        # the reference's loop
+        env = Race(timeout=timeout, cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
+        pol = RecurrentArgmaxPolicy(2, B, 20, seed=1)
+        states, any_valid = env.reset(tracks)
+        while any_valid and not env.finished():
+            states, rewards = env.step(pol(states))
+        # the graphed loop, fresh policy state
+        env2 = Race(timeout=timeout, cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
+        pol2 = RecurrentArgmaxPolicy(2, B, 20, seed=1)
+        states2, _ = env2.reset(tracks)
+        roll = GraphedRollout(env2, pol2, steps_per_replay=k, on_reset=pol2.reset)
+        roll.run(states2)
+    assert env2.finished() and env.finished()
+    assert env2.steps == env.steps, (env2.steps, env.steps)
+    for a, b in ((env.positions, env2.positions), (env.directions, env2.directions), (env.speeds, env2.speeds),
+                 (env.alive, env2.alive), (env.finishes, env2.finishes), (env.scores, env2.scores)):
+        assert eq(a, b)
+    assert eq(env.winners(), env2.winners())
+    if timeout > 10:
+        assert int(env.finishes.sum()) + int((~env.alive).sum()) > 0
