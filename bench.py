@@ -346,6 +346,74 @@ def run_b200(args, rank, world):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# config 3: whole-episode rollout with recurrent policies (informational, `--workload rollout`)
+# ------------------------------------------------------------------------------------------------
+class LstmAgents(object):
+    """P independent LSTMPolicy(20, 9)-shaped networks (policies/LSTMPolicy.py:6-41: two LSTMCell(256) + linear
+    heads, Gumbel-max sampling as in agents/PPOAgent.py:55-63), random weights, recurrent state updated in place."""
+
+    def __init__(self, P, B, device, seed=0):
+        torch.manual_seed(seed)
+        self.cells = [[torch.nn.LSTMCell(20 if i == 0 else 256, 256).to(device) for i in range(2)] for _ in range(P)]
+        self.heads = [torch.nn.Linear(256, 9).to(device) for _ in range(P)]
+        self.h = [[(torch.zeros(B, 256, device=device), torch.zeros(B, 256, device=device)) for _ in range(2)]
+                  for _ in range(P)]
+
+    def reset(self):
+        for per_player in self.h:
+            for h, c in per_player:
+                h.zero_(); c.zero_()
+
+    def __call__(self, states):
+        acts = []
+        for p in range(len(self.cells)):
+            x = states[p]
+            for i, cell in enumerate(self.cells[p]):
+                h, c = cell(x, self.h[p][i])
+                self.h[p][i][0].copy_(h); self.h[p][i][1].copy_(c)
+                x = h
+            logits = self.heads[p](x)
+            logits[:, 1] += 2.0                                    # untrained nets: bias to "forward" so that cars travel
+            gumbel = -torch.log(-torch.log(torch.rand_like(logits).clamp_min(1e-20)))
+            acts.append(torch.argmax(logits + gumbel, dim=-1))
+        return torch.stack(acts, 0)
+
+
+def run_rollout_workload(args):
+    """train-gan.py:86-104 on synthetic boards: reset, play the episode with 2 LSTM agents, winner statistics.
+    Prints one JSON line comparing the reference-style per-step loop with GraphedRollout."""
+    from game_level_gan_b200.games import GraphedRollout, Race, RaceConfig
+    device = torch.device('cuda', 0)
+    torch.cuda.set_device(0)
+    B, T_limit = 2060, 500                                          # (1024 generated + 6 predefined) x 2 mirrored
+    tracks = synthetic_tracks(B, SEED)
+    out = {'workload': 'config3: episode rollout, %d boards x 2 LSTM(256x2) agents, <= %d steps' % (B, T_limit)}
+    with torch.no_grad():
+        for mode in ('loop', 'graph'):
+            env = Race(timeout=T_limit / 20. - 0.025, cars=RaceConfig.cars, framerate=1. / 20., log_history=False, device=device)
+            agents = LstmAgents(2, B, device)
+            best = None
+            for rep in range(3):
+                states, any_valid = env.reset(tracks)
+                agents.reset()
+                roll = GraphedRollout(env, agents, steps_per_replay=16, on_reset=agents.reset).capture() if mode == 'graph' else None
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                if mode == 'loop':
+                    while any_valid and not env.finished():
+                        states, rewards = env.step(agents(states))
+                else:
+                    roll.run(states)
+                stats = env.winner_stats(1)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            out[mode] = {'episode_ms': 1e3 * best, 'steps': env.steps, 'us_per_step': 1e6 * best / max(env.steps - 1, 1),
+                         'env_steps_per_s': (env.steps - 1) * B * 2 / best, 'finished_frac': float(env.finishes.float().mean())}
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -356,10 +424,18 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--replicas', type=int, default=REPLICAS, help='independent config-2 batches stepped round-robin')
     ap.add_argument('--tracks', type=int, default=4096, help='tracks per batch (default = config 2)')
+    ap.add_argument('--workload', default='step', choices=['step', 'rollout'],
+                    help="'rollout': config 3 (episode with LSTM agents), informational, not the contract line")
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     globals()['B_TRACKS'] = args.tracks
+    if args.workload == 'rollout':
+        if rank == 0:
+            import __graft_entry__ as entry
+            entry.build()
+            run_rollout_workload(args)
+        return
     if args.impl == 'reference':
         if args.steps > 400:
             args.steps = 200          # bounded: ~0.1 s per sampled step on the host
