@@ -420,7 +420,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20000)
     ap.add_argument('--warmup', type=int, default=200)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--variant', default='fast', choices=['fast', 'brute'])
+    ap.add_argument('--variant', default='fast', choices=['fast', 'warp', 'scan', 'brute'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--replicas', type=int, default=REPLICAS, help='independent config-2 batches stepped round-robin')
     ap.add_argument('--tracks', type=int, default=4096, help='tracks per batch (default = config 2)')

@@ -12,8 +12,8 @@ LIB_PATH = os.path.join(HERE, 'csrc', 'libglg_b200.so')
 MAX_PLAYERS = 8
 MAX_RAYS = 32
 ALIVE_SLOTS = 64
-STEP_FAST, STEP_BRUTE, STEP_SCAN = 0, 1, 2
-ABI_VERSION = 4
+STEP_FAST, STEP_BRUTE, STEP_SCAN, STEP_PACKED = 0, 1, 2, 3
+ABI_VERSION = 5
 
 
 class GlgError(RuntimeError):

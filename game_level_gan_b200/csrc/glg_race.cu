@@ -74,6 +74,12 @@ __device__ __forceinline__ void record_copy_wait(uint64_t* bar) {
     }
 }
 
+}  // namespace glg
+
+#include "glg_race_packed.cuh"
+
+namespace glg {
+
 // OC: number of rays known at compile time (0 = generic)
 #ifndef GLG_STEP_MINBLOCKS
 #define GLG_STEP_MINBLOCKS 6     // 256-thread blocks per SM the register allocator targets (6 -> 40 registers, 50 warps/SM;
@@ -340,10 +346,10 @@ static int check_step_args(const glg_race_params* pr, const float* geom, int B, 
                            const void* valid, const void* extent, int variant, const glg_race_state& st,
                            const void* so, const void* ro)
 {
-    GLG_REQUIRE(variant == GLG_STEP_FAST || variant == GLG_STEP_BRUTE || variant == GLG_STEP_SCAN,
+    GLG_REQUIRE(variant == GLG_STEP_FAST || variant == GLG_STEP_BRUTE || variant == GLG_STEP_SCAN || variant == GLG_STEP_PACKED,
                 "glg_race_step: unknown variant %d", variant);
-    GLG_REQUIRE(variant != GLG_STEP_FAST || extent != nullptr || B == 0,
-                "glg_race_step: GLG_STEP_FAST needs the track extents (glg_track_extent)");
+    GLG_REQUIRE((variant != GLG_STEP_FAST && variant != GLG_STEP_PACKED) || extent != nullptr || B == 0,
+                "glg_race_step: GLG_STEP_PACKED / GLG_STEP_FAST need the track extents (glg_track_extent)");
     GLG_REQUIRE(pr != nullptr, "glg_race_step: params is null");
     GLG_REQUIRE(pr->num_players >= 1 && pr->num_players <= GLG_MAX_PLAYERS, "glg_race_step: num_players %d out of range", pr->num_players);
     GLG_REQUIRE(pr->num_rays >= 1 && pr->num_rays <= GLG_MAX_RAYS, "glg_race_step: num_rays %d out of range", pr->num_rays);
@@ -375,8 +381,34 @@ static void launch_one(const glg_race_params* pr, const StepArgs& a, cudaStream_
     cudaLaunchKernelEx(&cfg, race_step_kernel<VARIANT, OC>, *pr, a);
 }
 
+template <int TPB>
+static void launch_packed(const glg_race_params* pr, const StepArgs& a, cudaStream_t stream)
+{
+    const int WPT = (pr->num_players + 1) / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((a.B + TPB - 1) / TPB);
+    cfg.blockDim = dim3(32 * WPT * TPB);
+    cfg.dynamicSmemBytes = TPB * pk_track_bytes(a.N, 2 * WPT);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cap);
+    cfg.attrs = attr;
+    cfg.numAttrs = cap == cudaStreamCaptureStatusNone ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, race_step_packed_kernel<TPB>, *pr, a);
+}
+
 static int launch_step(const glg_race_params* pr, const StepArgs& a, int variant, cudaStream_t stream)
 {
+    // PACKED (two cars per warp) is written for 18 rays and at most 32 half-warp passes over the polyline
+    if (variant == GLG_STEP_PACKED && (pr->num_rays != 18 || a.N > 256)) variant = GLG_STEP_FAST;
+    if (variant == GLG_STEP_PACKED) {
+        if (pr->num_players <= 2) launch_packed<2>(pr, a, stream);
+        else launch_packed<1>(pr, a, stream);
+        return GLG_OK;
+    }
     if (variant == GLG_STEP_FAST && pr->num_rays != 18) variant = GLG_STEP_SCAN;    // stage 1 is written for 9 ray lines
     if (variant == GLG_STEP_SCAN && (pr->num_rays & 1)) variant = GLG_STEP_BRUTE;   // pruning pairs opposite rays
     if (variant == GLG_STEP_SCAN && (2 * a.N - 1 + 30) / 31 > 32) variant = GLG_STEP_BRUTE;   // 32-bit pass bitmap

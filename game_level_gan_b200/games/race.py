@@ -104,7 +104,7 @@ class Race(MultiEnvironment):
         return self._const[key]
 
     def _variant_code(self):
-        return {'fast': _lib.STEP_FAST, 'brute': _lib.STEP_BRUTE, 'scan': _lib.STEP_SCAN}[self.variant]
+        return {'fast': _lib.STEP_PACKED, 'warp': _lib.STEP_FAST, 'brute': _lib.STEP_BRUTE, 'scan': _lib.STEP_SCAN}[self.variant]
 
     # ---- reference API -------------------------------------------------------------------------
     def state_shape(self):

@@ -31,9 +31,11 @@ extern "C" {
 #define GLG_ALIVE_SLOTS   64  /* int32 slots of the "somebody is alive" step stamp            */
 
 /* step kernel variants (all produce identical results; tests compare them) */
-#define GLG_STEP_FAST     0   /* two-stage exact pruning of the ray cast (production; 18 rays)   */
+#define GLG_STEP_FAST     0   /* two-stage exact pruning of the ray cast, one warp per car (18 rays) */
 #define GLG_STEP_BRUTE    1   /* every ray x every wall, the literal reference loop            */
 #define GLG_STEP_SCAN     2   /* single-pass exact angular pruning (any even number of rays)   */
+#define GLG_STEP_PACKED   3   /* production: GLG_STEP_FAST's algorithm with two cars per warp; falls back to
+                                 GLG_STEP_FAST / SCAN / BRUTE for ray counts and track lengths it does not cover */
 
 typedef void* glg_stream_t;   /* cudaStream_t */
 
@@ -118,7 +120,7 @@ int glg_race_init(glg_race_state state, int32_t B, int32_t P, int32_t* alive_sta
  * sensors, observation pack.
  *   actions    [P,B] i64 (values 0..8), not modified
  *   valid      [B] u8 (per track)
- *   extent     [B,2] f32 from glg_track_extent (required by GLG_STEP_FAST, else may be NULL)
+ *   extent     [B,2] f32 from glg_track_extent (required by GLG_STEP_PACKED / FAST, else may be NULL)
  *   step_no    value of Race.steps AFTER the increment of this step (race.py:349)
  *   states_out [P,B,num_rays+2] f32, rewards_out [P,B] f32
  *   alive_stamp [GLG_ALIVE_SLOTS] i32 or NULL: slot (b % 64) := max(slot, launch_seq) if track b still
@@ -130,7 +132,7 @@ int glg_race_init(glg_race_state state, int32_t B, int32_t P, int32_t* alive_sta
  *              out, race.py:502-504) does nothing, so a graph may run past the end of the episode.
  *   history    optional [>= step_no+1, P, 6] f32 ring written for track `record_id`
  *              (x, y, dx, dy, masked action, alive) at row step_no (race.py:492-494), or NULL
- *   variant    GLG_STEP_FAST, GLG_STEP_SCAN or GLG_STEP_BRUTE (identical results)                */
+ *   variant    GLG_STEP_PACKED, GLG_STEP_FAST, GLG_STEP_SCAN or GLG_STEP_BRUTE (identical results)  */
 int glg_race_step(const glg_race_params* params, const float* geom, int32_t B, int32_t N,
                   const int64_t* actions, const uint8_t* valid, const float* extent, glg_race_state state,
                   int32_t step_no, float* states_out, float* rewards_out,

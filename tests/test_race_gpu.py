@@ -43,7 +43,7 @@ def replay(case, env, geometry=None, exact=True):
     return bad
 
 
-@pytest.mark.parametrize('variant', ['fast', 'scan', 'brute'])
+@pytest.mark.parametrize('variant', ['fast', 'warp', 'scan', 'brute'])
 @pytest.mark.parametrize('name', QUANTISED)
 def test_fixture_bit_exact_end_to_end(name, variant):
     """Generator-like tracks (arcs in 1/4 steps): geometry, every step output and the winners are
@@ -57,7 +57,7 @@ def test_fixture_bit_exact_end_to_end(name, variant):
     assert eq(env.winners(), c['winners'])
 
 
-@pytest.mark.parametrize('variant', ['fast', 'scan', 'brute'])
+@pytest.mark.parametrize('variant', ['fast', 'warp', 'scan', 'brute'])
 def test_fixture_float_tracks(variant):
     """Arbitrary float arcs/widths: step parity is bit-exact on the reference's geometry; the build
     itself differs from the reference's SLEEF sin/cos by a few ulp (tolerance 2e-5 absolute)."""
@@ -122,7 +122,7 @@ def test_free_running_rollout_vs_c_oracle(P):
     acts = torch.randint(0, 9, (T, P, B), generator=g)
     acts = torch.where(torch.rand((T, P, B), generator=g) < 0.5, torch.ones_like(acts), acts)
     envs = {v: Race(timeout=40., cars=[RaceCar(*c) for c in cars], framerate=1. / 20., log_history=False,
-                    variant=v) for v in ('fast', 'scan', 'brute')}
+                    variant=v) for v in ('fast', 'warp', 'scan', 'brute')}
     orc = _c_oracle_for(None, cars, 1. / 20., 40.)
     st, ct, _ = _tables.heading_tables(128)
     so, _ = orc.reset(tracks.numpy(), st.numpy(), ct.numpy())
@@ -139,7 +139,7 @@ def test_free_running_rollout_vs_c_oracle(P):
             bad[v] += nmismatch(sg, so) + nmismatch(rg, ro_)
             bad[v] += nmismatch(env.positions, orc.pos) + nmismatch(env.speeds, orc.speed)
             bad[v] += nmismatch(env._alive, orc.alive) + nmismatch(env.scores, orc.scores)
-    assert bad == {'fast': 0, 'scan': 0, 'brute': 0}, bad
+    assert bad == {'fast': 0, 'warp': 0, 'scan': 0, 'brute': 0}, bad
     for env in envs.values():
         assert eq(env.winners(), orc.winners())
     assert int(orc.alive.sum()) < B * P            # the rollout really killed cars
