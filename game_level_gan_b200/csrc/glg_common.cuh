@@ -40,6 +40,10 @@ __device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %
 #define GLG_TRACE(slot) do {} while (0)
 #endif
 
+#ifndef GLG_CHAIN_BACKOFF_NS
+#define GLG_CHAIN_BACKOFF_NS 200    // sleep between polls of a chained car's stamp (glg_race_rollout)
+#endif
+
 constexpr unsigned FULL = 0xffffffffu;
 constexpr float INF = __builtin_huge_valf();
 

@@ -136,8 +136,10 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
             int spin = 0;
             do {
                 asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(a.chain + k) : "memory");
-                if (++spin > (1 << 24)) __trap();
-            } while (got != want);
+                if (got == want) break;
+                __nanosleep(GLG_CHAIN_BACKOFF_NS);                         // do not burn issue slots while waiting
+                if (++spin > (1 << 22)) __trap();
+            } while (true);
         }
         __syncwarp();
     } else {
@@ -388,7 +390,15 @@ static void launch_packed(const glg_race_params* pr, const StepArgs& a, cudaStre
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((a.B + TPB - 1) / TPB);
     cfg.blockDim = dim3(32 * WPT * TPB);
-    cfg.dynamicSmemBytes = TPB * pk_track_bytes(a.N, 2 * WPT);
+    // Measured (chained rollouts, config 2): throughput peaks at ~16 resident 64-thread CTAs per SM and falls
+    // off on both sides (14: -3 %, 21: -13 %), so the launch asks for at least 1/16 of the SM's shared memory.
+    static const int ctas = getenv("GLG_PACKED_CTAS_PER_SM") ? atoi(getenv("GLG_PACKED_CTAS_PER_SM")) : 16;
+    size_t smem = (size_t)TPB * pk_track_bytes(a.N, 2 * WPT);
+    if (ctas > 0) {
+        const size_t share = ((size_t)(228 * 1024) / (size_t)ctas - 1024) & ~(size_t)127;   // 1 KB per CTA is reserved by the system
+        if (smem < share) smem = share;
+    }
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

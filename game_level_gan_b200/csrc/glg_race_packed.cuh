@@ -27,14 +27,17 @@ struct PackedCar {                             // per-car shared scratch
     unsigned pad[3];
 };
 
-// shared memory per track: [record 3N float2][mbarrier 16 B][cars x PackedCar][cars x (wlist u16[LL], cq u16[LL])]
-// LL = max(list_len(N), PK_QCAP): the second list holds the collision walls first and the candidate queue later.
-__host__ __device__ inline int pk_list_len(int N) { const int a = list_len(N); return a > PK_QCAP ? a : PK_QCAP; }
-__host__ __device__ inline size_t pk_cars_offset(int N) { return smem_barrier_offset(N) + 16; }
-__host__ __device__ inline size_t pk_lists_offset(int N, int cars) { return pk_cars_offset(N) + (size_t)cars * sizeof(PackedCar); }
-__host__ __device__ inline size_t pk_track_bytes(int N, int cars) {
-    const size_t x = pk_lists_offset(N, cars) + (size_t)cars * 2 * pk_list_len(N) * sizeof(unsigned short);
-    return (x + 127) & ~(size_t)127;
+// shared memory per track: [record 3N float2][mbarrier 16 B][cars x PackedCar][cars x cq u16[LL]][cars x wlist u16[2N]]
+// LL = max(list_len(N), PK_QCAP): cq holds the collision walls first and the candidate queue later.  With one
+// warp per track (P <= 2) the two wall lists (2 x 2N u16 = 8N bytes) live in the record's centre points, which
+// nobody reads after the progress arg-min, and the last block is not allocated.
+__host__ __device__ inline unsigned pk_list_len(int N) { const int a = list_len(N); return a > PK_QCAP ? a : PK_QCAP; }
+__host__ __device__ inline unsigned pk_cars_offset(int N) { return (unsigned)smem_barrier_offset(N) + 16u; }
+__host__ __device__ inline unsigned pk_cq_offset(int N, int cars) { return pk_cars_offset(N) + (unsigned)cars * (unsigned)sizeof(PackedCar); }
+__host__ __device__ inline unsigned pk_wlist_offset(int N, int cars) { return pk_cq_offset(N, cars) + (unsigned)cars * pk_list_len(N) * 2u; }
+__host__ __device__ inline unsigned pk_track_bytes(int N, int cars) {
+    const unsigned x = cars == 2 ? pk_wlist_offset(N, cars) : pk_wlist_offset(N, cars) + (unsigned)cars * 2u * (unsigned)N * 2u;
+    return (x + 127u) & ~127u;
 }
 
 __device__ __forceinline__ unsigned group_ballot(bool pred, int grp) {
@@ -101,10 +104,11 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
     constexpr int O = PK_RAYS;
     const int N = a.N, B = a.B, V = 2 * N;
     const int P = pr.num_players;
-    const int WPT = (P + 1) >> 1;
+    // TPB == 2 is launched for P <= 2 only: one warp per track, two tracks per CTA
+    const int WPT = (TPB == 2) ? 1 : (P + 1) >> 1;
     const int warp = threadIdx.x >> 5, lane = lane_id();
-    const int tslot = (TPB == 1) ? 0 : warp / WPT;
-    const int wt = warp - tslot * WPT;
+    const int tslot = (TPB == 2) ? warp : 0;
+    const int wt = (TPB == 2) ? 0 : warp;
     const int b = blockIdx.x * TPB + tslot;
     const int grp = lane >> 4, gl = lane & 15;
     const unsigned gmask = 0xffffu << (grp * PK_G);
@@ -114,12 +118,15 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
     const bool car_on = track_on && p < P;
     const int cars = 2 * WPT;
 
-    unsigned char* tbase = smem_raw + (size_t)tslot * pk_track_bytes(N, cars);
+    const int ci = wt * 2 + grp;                                          // car slot within the track
+    unsigned char* tbase = smem_raw + (unsigned)tslot * pk_track_bytes(N, cars);
     float2* pts = reinterpret_cast<float2*>(tbase);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(tbase + smem_barrier_offset(N));
-    PackedCar* car = reinterpret_cast<PackedCar*>(tbase + pk_cars_offset(N)) + (wt * 2 + grp);
-    unsigned short* wlist = reinterpret_cast<unsigned short*>(tbase + pk_lists_offset(N, cars)) + (size_t)(wt * 2 + grp) * 2 * pk_list_len(N);
-    unsigned short* cq = wlist + pk_list_len(N);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tbase + (unsigned)smem_barrier_offset(N));
+    PackedCar* car = reinterpret_cast<PackedCar*>(tbase + pk_cars_offset(N)) + ci;
+    unsigned short* cq = reinterpret_cast<unsigned short*>(tbase + pk_cq_offset(N, cars)) + (unsigned)ci * pk_list_len(N);
+    unsigned short* wlist = (TPB == 2)
+        ? reinterpret_cast<unsigned short*>(pts + 2 * N) + (unsigned)grp * 2u * (unsigned)N     // over the centre points
+        : reinterpret_cast<unsigned short*>(tbase + pk_wlist_offset(N, cars)) + (unsigned)ci * 2u * (unsigned)N;
 
     // ---- stage the track record with one bulk async copy per track ----
     const uint32_t rec_bytes = (uint32_t)(3 * N * sizeof(float2));
@@ -133,8 +140,10 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
             int got, spin = 0;
             do {
                 asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(a.chain + k) : "memory");
-                if (++spin > (1 << 24)) __trap();
-            } while (got != want);
+                if (got == want) break;
+                __nanosleep(GLG_CHAIN_BACKOFF_NS);                         // do not burn issue slots while waiting
+                if (++spin > (1 << 22)) __trap();
+            } while (true);
         }
         __syncwarp();
     } else {
@@ -205,6 +214,8 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
             if (tie) idx = f2;
         }
     }
+
+    __syncwarp();                        // (P <= 2) the centre points become the wall lists from here on
 
     // ---- scan: preconditions, ray table, stage 1 over all vertices ----
     float reward = fin ? 0.f : pr.step_penalty;                            // race.py:382-383
