@@ -65,6 +65,34 @@ __device__ __forceinline__ bool segments_cross(P2 p, P2 q, P2 a, P2 b) {
     return hit || so;
 }
 
+// Same result as ray_wall_t below, arranged for the common case: when none of the four orientation values is
+// zero, no special case of games/race.py:256-267 can fire and the general case is a test of sign BITS.
+__device__ __forceinline__ float ray_wall_t_fast(P2 p, P2 q, P2 s, P2 d, P2 f) {
+    const float wqx = xsub(q.x, p.x), wqy = xsub(q.y, p.y);
+    const float fsx = xsub(f.x, s.x), fsy = xsub(f.y, s.y);
+    const float v1 = det2(wqy, xsub(s.x, q.x), wqx, xsub(s.y, q.y));       // turn_val(p, q, s)
+    const float v2 = det2(wqy, xsub(f.x, q.x), wqx, xsub(f.y, q.y));       // turn_val(p, q, f)
+    const float v3 = det2(fsy, xsub(p.x, f.x), fsx, xsub(p.y, f.y));       // turn_val(s, f, p)
+    const float v4 = det2(fsy, xsub(q.x, f.x), fsx, xsub(q.y, f.y));       // turn_val(s, f, q)
+    const float INF_ = __int_as_float(0x7f800000);
+    bool hit, so = false;
+    if (fabsf(v1) > 0.f && fabsf(v2) > 0.f && fabsf(v3) > 0.f && fabsf(v4) > 0.f) {   // false for +-0 and for NaN
+        const unsigned x = (__float_as_uint(v1) ^ __float_as_uint(v2)) & (__float_as_uint(v3) ^ __float_as_uint(v4));
+        hit = (x >> 31) != 0u;                                  // o1 != o2 && o3 != o4 with all four non-zero
+    } else {
+        hit = cross_tables(p, q, s, f, so);
+        hit = hit && !so;
+    }
+    const float psx = xsub(p.x, s.x), psy = xsub(p.y, s.y);
+    const float num = det2(psy, wqx, psx, wqy);                 // :300
+    const float den = det2(d.y, wqx, d.x, wqy);                 // :301
+    float t = INF_;
+    if (so) t = 0.f;                                            // :303
+    else if (hit) t = xdiv(num, den);                           // :304
+    if (t < 0.f) t = INF_;                                      // :306
+    return t;
+}
+
 // ray parameter t of wall (p,q) for the ray (s, d) with far point f, games/race.py:287-306.
 // Returns +inf for "no hit"; may return NaN (0/0) exactly where the reference does.
 __device__ __forceinline__ float ray_wall_t(P2 p, P2 q, P2 s, P2 d, P2 f) {

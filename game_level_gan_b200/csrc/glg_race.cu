@@ -21,6 +21,8 @@ namespace glg {
 
 // action a -> throttle flag index a % 3 (0, +1, -3) and steering flag index a / 3 (0, +1, -1), games/race.py:52-71
 
+struct PackedLayout { unsigned bar_off, cars_off, cq_off, wlist_off, list_len, track_bytes; };   // glg_race_packed.cuh
+
 struct StepArgs {
     const float* geom;
     const int64_t* actions;
@@ -37,6 +39,7 @@ struct StepArgs {
     int32_t seq;          // launch sequence number (unique, increasing per environment)
     int32_t chained;      // wait for chain[car] == seq-1 instead of for the whole previous grid
     int32_t early;        // publish chain[car] right after the state write-back (outputs of different steps do not alias)
+    PackedLayout pk;      // filled by launch_packed
 };
 
 __global__ void race_init_kernel(glg_race_state st, int K, int32_t* alive_stamp)
@@ -407,7 +410,9 @@ static void launch_packed(const glg_race_params* pr, const StepArgs& a, cudaStre
     cudaStreamIsCapturing(stream, &cap);
     cfg.attrs = attr;
     cfg.numAttrs = cap == cudaStreamCaptureStatusNone ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, race_step_packed_kernel<TPB>, *pr, a);
+    StepArgs ap = a;
+    ap.pk = pk_layout(a.N, 2 * WPT);
+    cudaLaunchKernelEx(&cfg, race_step_packed_kernel<TPB>, *pr, ap);
 }
 
 static int launch_step(const glg_race_params* pr, const StepArgs& a, int variant, cudaStream_t stream)
@@ -469,7 +474,7 @@ extern "C" int glg_race_step(const glg_race_params* params, const float* geom, i
     const int rc = check_step_args(params, geom, B, N, actions, valid, extent, variant, state, states_out, rewards_out);
     if (rc != GLG_OK || B == 0) return rc;
     StepArgs a{geom, actions, valid, extent, state, states_out, rewards_out, alive_stamp, history, nullptr, base,
-               B, N, step_no, record_id, launch_seq, 0, 0};
+               B, N, step_no, record_id, launch_seq, 0, 0, {}};
     launch_step(params, a, variant, (cudaStream_t)stream);
     return launch_status("glg_race_step");
 }
@@ -491,7 +496,7 @@ extern "C" int glg_race_rollout(const glg_race_params* params, const float* geom
                    keep_all ? states_out + (size_t)t * PB * W : states_out,
                    keep_all ? rewards_out + (size_t)t * PB : rewards_out,
                    alive_stamp, nullptr, chain, nullptr, B, N, first_step_no + t, -1, first_launch_seq + t,
-                   (chain != nullptr && t > 0) ? 1 : 0, keep_all ? 1 : 0};
+                   (chain != nullptr && t > 0) ? 1 : 0, keep_all ? 1 : 0, {}};
         launch_step(params, a, variant, (cudaStream_t)stream);
     }
     return launch_status("glg_race_rollout");

@@ -84,6 +84,17 @@ __device__ __noinline__ bool packed_collide_brute(const TrackView& tv, P2 op, P2
     return group_ballot(hit, grp) != 0u;
 }
 
+__host__ inline PackedLayout pk_layout(int N, int cars) {
+    PackedLayout l;
+    l.bar_off = (unsigned)smem_barrier_offset(N);
+    l.cars_off = pk_cars_offset(N);
+    l.cq_off = pk_cq_offset(N, cars);
+    l.wlist_off = pk_wlist_offset(N, cars);
+    l.list_len = pk_list_len(N);
+    l.track_bytes = pk_track_bytes(N, cars);
+    return l;
+}
+
 #ifndef GLG_PACKED_MINBLOCKS
 #define GLG_PACKED_MINBLOCKS 10     // 128-thread blocks per SM the register allocator targets (10 -> 48 registers)
 #endif
@@ -119,14 +130,15 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
     const int cars = 2 * WPT;
 
     const int ci = wt * 2 + grp;                                          // car slot within the track
-    unsigned char* tbase = smem_raw + (unsigned)tslot * pk_track_bytes(N, cars);
+    // shared-memory carve-up (byte offsets computed by the host, pk_layout)
+    unsigned char* tbase = smem_raw + (unsigned)tslot * a.pk.track_bytes;
     float2* pts = reinterpret_cast<float2*>(tbase);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(tbase + (unsigned)smem_barrier_offset(N));
-    PackedCar* car = reinterpret_cast<PackedCar*>(tbase + pk_cars_offset(N)) + ci;
-    unsigned short* cq = reinterpret_cast<unsigned short*>(tbase + pk_cq_offset(N, cars)) + (unsigned)ci * pk_list_len(N);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tbase + a.pk.bar_off);
+    PackedCar* car = reinterpret_cast<PackedCar*>(tbase + a.pk.cars_off) + ci;
+    unsigned short* cq = reinterpret_cast<unsigned short*>(tbase + a.pk.cq_off) + (unsigned)ci * a.pk.list_len;
     unsigned short* wlist = (TPB == 2)
         ? reinterpret_cast<unsigned short*>(pts + 2 * N) + (unsigned)grp * 2u * (unsigned)N     // over the centre points
-        : reinterpret_cast<unsigned short*>(tbase + pk_wlist_offset(N, cars)) + (unsigned)ci * 2u * (unsigned)N;
+        : reinterpret_cast<unsigned short*>(tbase + a.pk.wlist_off) + (unsigned)ci * 2u * (unsigned)N;
 
     // ---- stage the track record with one bulk async copy per track ----
     const uint32_t rec_bytes = (uint32_t)(3 * N * sizeof(float2));
@@ -429,7 +441,7 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
             P2 pp, qq;
             wall_by_line_index(tv, w, pp, qq);
             const float4 r = car->ray[i];
-            const float t = ray_wall_t(pp, qq, np, P2{r.x, r.y}, P2{r.z, r.w});
+            const float t = ray_wall_t_fast(pp, qq, np, P2{r.x, r.y}, P2{r.z, r.w});
             if (t != t) atomicOr(&car->nan_mask, 1u << i);
             else atomicMin(&car->tmin[i], __float_as_int(t));
         }
