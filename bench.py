@@ -326,6 +326,8 @@ def run_b200(args, rank, world):
                    'l2': '%d replicas stepped round-robin, %.0f MB of geometry > 126 MB L2 (no flush)'
                          % (REPLICAS, REPLICAS * ALGO_BYTES_PER_TRACK * B_TRACKS / 1e6),
                    'alive_fraction': [alive_start, alive_end],
+                   'launches': 'one step kernel per step (glg_race_rollout: chained car by car, every step writes its '
+                               'observations and rewards, keep_all=%s)' % KEEP_ALL,
                    'state_restore_every_steps': CYCLE, 'actions': 'heuristic-driver tape, race steps %d-%d' % (PREROLL, PREROLL + CYCLE), 'parallelism': 'dp%d (tracks sharded)' % world},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': ncu_traffic(), 'peak_source': peak_kind,

@@ -19,6 +19,10 @@ namespace glg {
 constexpr int PK_G = 16;                       // lanes per car
 constexpr int PK_QCAP = 288;                   // (wall, ray) candidates per car kept before the car falls back to brute force
 constexpr int PK_RAYS = 18;                    // stage 1 is written for 9 ray lines
+#ifndef GLG_S1_UNROLL
+#define GLG_S1_UNROLL 3
+#endif
+constexpr int PK_S1_UNROLL = GLG_S1_UNROLL;    // unroll factor of the stage-1 vertex loop
 
 struct PackedCar {                             // per-car shared scratch
     float4 ray[PK_RAYS];                       // dx, dy, far x, far y
@@ -253,7 +257,7 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
     const float Kn = scan_on ? 9.f * EPS_PERP * 1.4143f * 1.001f : 0.f;
     const int passes = (V + PK_G - 1) / PK_G;                              // <= 32 (the host routes N > 256 elsewhere)
     unsigned sbits = 0, fbits = 0, cbits = 0;
-#pragma unroll 3
+#pragma unroll PK_S1_UNROLL
     for (int pass = 0; pass < passes; ++pass) {
         const float2 pt = tv.line[pass * PK_G + gl];
         const float ux = pt.x - np.x, uy = pt.y - np.y;
