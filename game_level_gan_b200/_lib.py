@@ -46,6 +46,7 @@ SYMBOLS = {
     'glg_last_error': (ctypes.c_char_p, []),
     'glg_abi_version': (ctypes.c_int, []),
     'glg_track_build': (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
+    'glg_track_build_levels': (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     'glg_track_validate': (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp]),
     'glg_track_extent': (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp]),
     'glg_race_init': (ctypes.c_int, [RaceState, _i32, _i32, _vp, _vp]),

@@ -395,7 +395,8 @@ static void launch_packed(const glg_race_params* pr, const StepArgs& a, cudaStre
     cfg.blockDim = dim3(32 * WPT * TPB);
     // Measured (chained rollouts, config 2): throughput peaks at ~16 resident 64-thread CTAs per SM and falls
     // off on both sides (14: -3 %, 21: -13 %), so the launch asks for at least 1/16 of the SM's shared memory.
-    static const int ctas = getenv("GLG_PACKED_CTAS_PER_SM") ? atoi(getenv("GLG_PACKED_CTAS_PER_SM")) : 16;
+    // (only the two-tracks-per-CTA shape; one track of 4 cars per CTA is fastest unconstrained: 9.7e8 vs 9.3e8)
+    static const int ctas = getenv("GLG_PACKED_CTAS_PER_SM") ? atoi(getenv("GLG_PACKED_CTAS_PER_SM")) : (TPB == 2 ? 16 : 0);
     size_t smem = (size_t)TPB * pk_track_bytes(a.N, 2 * WPT);
     if (ctas > 0) {
         const size_t share = ((size_t)(228 * 1024) / (size_t)ctas - 1024) & ~(size_t)127;   // 1 KB per CTA is reserved by the system
@@ -418,7 +419,9 @@ static void launch_packed(const glg_race_params* pr, const StepArgs& a, cudaStre
 static int launch_step(const glg_race_params* pr, const StepArgs& a, int variant, cudaStream_t stream)
 {
     // PACKED (two cars per warp) is written for 18 rays and at most 32 half-warp passes over the polyline
-    if (variant == GLG_STEP_PACKED && (pr->num_rays != 18 || a.N > 256)) variant = GLG_STEP_FAST;
+    // (and stages the record with a bulk copy: 16-byte granular records only, i.e. even N)
+    if (variant == GLG_STEP_PACKED && (pr->num_rays != 18 || a.N > 256 || (a.N & 1) || ((uintptr_t)a.geom & 15u)))
+        variant = GLG_STEP_FAST;
     if (variant == GLG_STEP_PACKED) {
         if (pr->num_players <= 2) launch_packed<2>(pr, a, stream);
         else launch_packed<1>(pr, a, stream);

@@ -20,7 +20,7 @@ constexpr int BUILD_WARPS = 4;
 // running sum in double, every prefix rounded to float - therefore one lane walks
 // the 130 elements; everything else (sin/cos, normals, offsets, stores) is lane-parallel.
 __global__ void __launch_bounds__(BUILD_WARPS * 32)
-track_build_kernel(const float* __restrict__ tracks, int B, int L,
+track_build_kernel(const float* __restrict__ tracks, const uint8_t* __restrict__ levels, int B, int L,
                    const float* __restrict__ sin_table, const float* __restrict__ cos_table,
                    int table_half, float* __restrict__ geom)
 {
@@ -30,15 +30,21 @@ track_build_kernel(const float* __restrict__ tracks, int B, int L,
     const int wib = threadIdx.x >> 5;
     const int b = blockIdx.x * BUILD_WARPS + wib;
     if (b >= B) return;                                   // whole warp leaves together
-    float* head = smem + wib * 5 * N;                     // [N] heading prefix (in arc units)
-    float2* seg = reinterpret_cast<float2*>(head + N);    // [N] segment vectors
-    float2* cen = seg + N;                                // [N] centre points
+    const int Np = (N + 1) & ~1;                          // even, so that the float2 arrays stay 8-byte aligned
+    float* head = smem + wib * 5 * Np;                    // [N] heading prefix (in arc units)
+    float2* seg = reinterpret_cast<float2*>(head + Np);   // [N] segment vectors
+    float2* cen = seg + Np;                               // [N] centre points
     const float2* trk = reinterpret_cast<const float2*>(tracks) + (size_t)b * L;
+    // generator levels: segment j-1 is nibble (j-1)&1 of byte (j-1)>>1, arc = (level - 4) / 4, width 0
+    const uint8_t* lev = levels ? levels + (size_t)b * ((L + 1) >> 1) : nullptr;
 
     // sentinels (race.py:136-138) + "all arcs are multiples of 1/4" test for the table path
     bool quant = sin_table != nullptr;
     for (int j = lane; j < N; j += 32) {
-        const float arc = (j >= 1 && j <= L) ? __ldg(&trk[j - 1]).x : 0.f;
+        float arc = 0.f;
+        if (j >= 1 && j <= L)
+            arc = lev ? (float)((int)((__ldg(&lev[(j - 1) >> 1]) >> (4 * ((j - 1) & 1))) & 15) - 4) * 0.25f
+                      : __ldg(&trk[j - 1]).x;
         head[j] = arc;
         const float a4 = arc * 4.f;
         if (a4 != rintf(a4) || fabsf(a4) > 4.f) quant = false;
@@ -87,7 +93,7 @@ track_build_kernel(const float* __restrict__ tracks, int B, int L,
             const float nx = xadd(s1.y, s0.y);            // perp = (y, -x)
             const float ny = xadd(-s1.x, -s0.x);
             const float len = norm2(nx, ny);
-            const float wid = (j >= 2 && j - 1 <= L) ? __ldg(&trk[j - 2]).y : 0.f;
+            const float wid = (!lev && j >= 2 && j - 1 <= L) ? __ldg(&trk[j - 2]).y : 0.f;
             const float w = xadd(0.5f, xmul(1.5f, wid));
             ox = xmul(xdiv(nx, len), w);
             oy = xmul(xdiv(ny, len), w);
@@ -202,11 +208,28 @@ extern "C" int glg_track_build(const float* tracks, int32_t B, int32_t L, const 
     GLG_REQUIRE((sin_table == nullptr) == (cos_table == nullptr), "glg_track_build: give both tables or none");
     if (B == 0) return GLG_OK;
     const int N = L + 2;
-    const size_t smem = (size_t)BUILD_WARPS * 5 * N * sizeof(float);
+    const size_t smem = (size_t)BUILD_WARPS * 5 * ((N + 1) & ~1) * sizeof(float);
     const int grid = (B + BUILD_WARPS - 1) / BUILD_WARPS;
     track_build_kernel<<<grid, BUILD_WARPS * 32, smem, (cudaStream_t)stream>>>(
-        tracks, B, L, sin_table, cos_table, table_half, geom);
+        tracks, nullptr, B, L, sin_table, cos_table, table_half, geom);
     return launch_status("glg_track_build");
+}
+
+extern "C" int glg_track_build_levels(const uint8_t* levels, int32_t B, int32_t L, const float* sin_table,
+                                      const float* cos_table, int32_t table_half, float* geom,
+                                      glg_stream_t stream)
+{
+    using namespace glg;
+    GLG_REQUIRE(B >= 0 && L >= 1 && L <= 510, "glg_track_build_levels: need B >= 0 and 1 <= L <= 510 (got B=%d L=%d)", B, L);
+    GLG_REQUIRE((B == 0) || (levels && geom), "glg_track_build_levels: null pointer");
+    GLG_REQUIRE((sin_table == nullptr) == (cos_table == nullptr), "glg_track_build_levels: give both tables or none");
+    if (B == 0) return GLG_OK;
+    const int N = L + 2;
+    const size_t smem = (size_t)BUILD_WARPS * 5 * ((N + 1) & ~1) * sizeof(float);
+    const int grid = (B + BUILD_WARPS - 1) / BUILD_WARPS;
+    track_build_kernel<<<grid, BUILD_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        nullptr, levels, B, L, sin_table, cos_table, table_half, geom);
+    return launch_status("glg_track_build_levels");
 }
 
 extern "C" int glg_track_validate(const float* geom, int32_t B, int32_t N, uint8_t* valid,

@@ -129,18 +129,39 @@ class Race(MultiEnvironment):
     def action_name(a):
         return Race.ACTION_NAMES[a]
 
-    def reset(self, tracks, geometry=None):
+    @staticmethod
+    def pack_levels(levels):
+        """[B, L] integer arc levels 0..8 (index into linspace(-1, 1, 9), the discrete generator's output,
+        generators/race_track_generator.py:250-261) -> [B, ceil(L/2)] uint8, two levels per byte."""
+        lv = levels.to(torch.uint8)
+        if lv.size(1) & 1:
+            lv = torch.cat((lv, torch.full_like(lv[:, :1], 4)), 1)
+        return (lv[:, 0::2] | (lv[:, 1::2] << 4)).contiguous()
+
+    def reset_levels(self, levels):
+        """`reset` from the generator's discrete output: `levels` [B, L] integers 0..8 (arc = (level-4)/4,
+        width 0).  Same result as reset(tracks) with tracks[..., 0] = linspace(-1, 1, 9)[levels]."""
+        levels = levels.to(self.device)
+        return self.reset(None, packed_levels=(self.pack_levels(levels), levels.size(1)))
+
+    def reset(self, tracks, geometry=None, packed_levels=None):
         """tracks [B, L, (arc, width)] -> (states [P,B,O+2], any_valid).  games/race.py:116-211.
 
         `geometry=(centre, left, right)` ([B,L+2,2] each) skips the build and uses the given
         polylines instead (parity tests isolate step parity from build parity this way).
+        `packed_levels=(uint8 [B, ceil(L/2)], L)`: see reset_levels.
         """
         dev = self.device
         lib = _lib.lib()
         stream = _lib.stream_ptr(dev)
         with torch.no_grad():
-            tracks = tracks.detach().to(device=dev, dtype=torch.float32).contiguous()
-            B, L = tracks.size(0), tracks.size(1)
+            if packed_levels is not None:
+                packed, L = packed_levels
+                packed = packed.to(device=dev, dtype=torch.uint8).contiguous()
+                B = packed.size(0)
+            else:
+                tracks = tracks.detach().to(device=dev, dtype=torch.float32).contiguous()
+                B, L = tracks.size(0), tracks.size(1)
             N, P = L + 2, self.num_players
             self.steps = 0
             self.num_tracks = B
@@ -149,6 +170,10 @@ class Race(MultiEnvironment):
             if geometry is not None:
                 centre, left, right = (g.to(device=dev, dtype=torch.float32) for g in geometry)
                 self._geom[:, 0], self._geom[:, 1], self._geom[:, 2] = right.flip(1), left, centre
+            elif packed_levels is not None:
+                st, ct, half = self._heading_tables(L)
+                check(lib.glg_track_build_levels(ptr(packed), B, L, ptr(st), ptr(ct), half, ptr(self._geom), stream),
+                      'glg_track_build_levels')
             else:
                 st, ct, half = self._heading_tables(L)
                 check(lib.glg_track_build(ptr(tracks), B, L, ptr(st), ptr(ct), half, ptr(self._geom), stream),

@@ -101,6 +101,15 @@ int glg_track_build(const float* tracks, int32_t B, int32_t L,
                     const float* sin_table, const float* cos_table, int32_t table_half,
                     float* geom, glg_stream_t stream);
 
+/* The same geometry straight from the generator's discrete output.  The reference's
+ * GeneratorNetworkConvDiscrete emits, per segment, one of the 9 arc levels linspace(-1, 1, 9) and width 0
+ * (generators/race_track_generator.py:250-261); `levels` holds the level index 0..8 of every segment, two per
+ * byte (segment s in bits 4*(s&1).. of byte s>>1 of the track's ceil(L/2) bytes): 64 B per track at L = 128
+ * instead of 1 KB.  Result identical to glg_track_build on tracks[..., 0] = (level - 4) / 4, tracks[..., 1] = 0. */
+int glg_track_build_levels(const uint8_t* levels, int32_t B, int32_t L,
+                           const float* sin_table, const float* cos_table, int32_t table_half,
+                           float* geom, glg_stream_t stream);
+
 /* Track validity = no proper crossing among the 2(L+1)+2 lines (walls, start, finish).
  * Replaces Race._is_correct, games/race.py:326-334 (IMPL_GPU branch of reset, :199-200).
  *   valid [B] u8 out                                                                         */

@@ -194,3 +194,35 @@ def test_empty_batch_and_errors():
         env.reset(torch.zeros(2, 600, 2))               # L beyond the kernel limit
     with pytest.raises(GlgError):
         Race(timeout=40., cars=RaceConfig.cars, device='cpu')
+
+
+def test_reset_from_generator_levels():
+    """geometry straight from the 4-bit arc levels of the discrete generator equals the geometry
+    built from the float tracks (and therefore the reference's, fixture iid9), odd L included."""
+    from game_level_gan_b200.games import Race, RaceConfig
+    c = load_case('iid9')
+    tracks = t(c['tracks'])
+    levels = torch.round(tracks[:, :, 0] * 4).long() + 4
+    assert int(levels.min()) >= 0 and int(levels.max()) <= 8
+    env = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
+    states, any_valid = env.reset_levels(levels)
+    assert eq(env.segments, c['centre']) and eq(env.left_vecs, c['left']) and eq(env.right_vecs, c['right'])
+    assert eq(env.valid, c['valid']) and eq(states, c['states'][0]) and any_valid == bool(c['any_valid'])
+    g = torch.Generator().manual_seed(3)
+    lv = torch.randint(0, 9, (33, 77), generator=g)
+    a = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
+    b = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
+    tr = torch.zeros(33, 77, 2)
+    tr[:, :, 0] = torch.linspace(-1., 1., 9)[lv]
+    sa, _ = a.reset(tr)
+    sb, _ = b.reset_levels(lv)
+    assert eq(a._geom, b._geom) and eq(sa, sb) and eq(a._valid_tracks, b._valid_tracks)
+    # odd L: the record is not 16-byte granular, the step kernels take their plain-load path
+    c2 = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False, variant='brute')
+    sc, _ = c2.reset(tr)
+    assert eq(sa, sc)
+    for s in range(25):
+        acts = torch.randint(0, 9, (2, 33), generator=g)
+        acts[:, ::2] = 1
+        (sa, ra), (sc, rc) = a.step(acts.cuda()), c2.step(acts.cuda())
+        assert eq(sa, sc) and eq(ra, rc) and eq(a.positions, c2.positions) and eq(a.scores, c2.scores)
