@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, 'csrc', 'libglg_b200.so')
 
 MAX_PLAYERS = 8
 MAX_RAYS = 32
-ALIVE_SLOTS = 64
+ALIVE_SLOTS = 1024
 STEP_FAST, STEP_BRUTE, STEP_SCAN, STEP_PACKED = 0, 1, 2, 3
 ABI_VERSION = 5
 

@@ -44,6 +44,14 @@ __host__ __device__ inline unsigned pk_track_bytes(int N, int cars) {
     return (x + 127u) & ~127u;
 }
 
+// min over the 16 lanes of a group (xor butterflies stay inside the group); redux.sync with two different
+// member masks in one warp takes the compiler's slow divergent path
+__device__ __forceinline__ unsigned group_min_u32(unsigned v) {
+#pragma unroll
+    for (int off = PK_G / 2; off > 0; off >>= 1) v = min(v, __shfl_xor_sync(FULL, v, off));
+    return v;
+}
+
 __device__ __forceinline__ unsigned group_ballot(bool pred, int grp) {
     return (__ballot_sync(FULL, pred) >> (grp * PK_G)) & 0xffffu;
 }
@@ -66,7 +74,7 @@ __device__ __noinline__ void packed_sensors_brute(const TrackView& tv, const glg
             else t = fminf(t, tw);
         }
         const unsigned anynan = __ballot_sync(FULL, nan) & gmask;
-        const float m = __uint_as_float(__reduce_min_sync(gmask, __float_as_uint(fmaxf(t, 0.f))));   // t in {-0} u [0, inf]
+        const float m = __uint_as_float(group_min_u32(__float_as_uint(fmaxf(t, 0.f))));   // t in {-0} u [0, inf]
         const bool negzero = (__ballot_sync(FULL, __float_as_uint(t) == 0x80000000u) & gmask) != 0u;
         if (wanted && gl == 0) {
             float r = (m == 0.f && negzero) ? -0.f : m;
@@ -100,12 +108,14 @@ __host__ inline PackedLayout pk_layout(int N, int cars) {
 }
 
 #ifndef GLG_PACKED_MINBLOCKS
-#define GLG_PACKED_MINBLOCKS 10     // 128-thread blocks per SM the register allocator targets (10 -> 48 registers)
+#define GLG_PACKED_MINBLOCKS 8      // 128-thread blocks per SM the register allocator targets: 8 -> 64 registers for the
+                                    // two-tracks-per-CTA shape (its residency is capped at 16 CTAs/SM anyway; 8.85e8 vs 8.6e8
+                                    // env-steps/s with 48), 10 -> 48 registers for one track of 3..8 cars per CTA
 #endif
 
 // TPB tracks per CTA; each track has WPT = ceil(P/2) consecutive warps.
 template <int TPB>
-__global__ void __launch_bounds__(128, GLG_PACKED_MINBLOCKS)
+__global__ void __launch_bounds__(128, TPB == 2 ? GLG_PACKED_MINBLOCKS : GLG_PACKED_MINBLOCKS + 2)
 race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -116,6 +126,7 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
         seq += __ldcg(a.base + 1);
         if (step_no > pr.steps_limit + 1) return;     // past the time limit: the step is a no-op
     }
+    GLG_MARK_INIT;
     constexpr int O = PK_RAYS;
     const int N = a.N, B = a.B, V = 2 * N;
     const int P = pr.num_players;
@@ -166,6 +177,7 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
         asm volatile("griddepcontrol.wait;" ::: "memory");
     }
 
+    GLG_MARK(0);
     // ---- car state and kinematics (uniform within a group) ----
     bool alive = false, fin = false, ok = false;
     int act = 0;
@@ -195,10 +207,12 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
     const P2 op{pos.x, pos.y};
     const P2 np{xadd(pos.x, xmul(nd.x, nv)), xadd(pos.y, xmul(nd.y, nv))};   // race.py:372
 
+    GLG_MARK(1);
     __syncthreads();                     // mbarrier init visible to the other warps of the track
     if (track_on) record_copy_wait(bar);
     const TrackView tv{pts, pts + 2 * N, N};
 
+    GLG_MARK(2);
     // ---- progress: FIRST arg-min of |np - centre_j| (race.py:374-376), see race_step_kernel ----
     int idx;
     {
@@ -211,9 +225,9 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
             if (q < q1) { q2 = q1; q1 = q; j1 = j; }
             else q2 = fminf(q2, q);
         }
-        const float qmin = __uint_as_float(__reduce_min_sync(gmask, __float_as_uint(q1)));     // q >= 0
+        const float qmin = __uint_as_float(group_min_u32(__float_as_uint(q1)));              // q >= 0
         const float qcut = qmin * 1.000001f + 1e-45f;
-        idx = (int)__reduce_min_sync(gmask, (q1 == qmin) ? (unsigned)j1 : 0x7fffffffu);
+        idx = (int)group_min_u32((q1 == qmin) ? (unsigned)j1 : 0x7fffffffu);
         // near ties of the ROUNDED norms: only if a second value lies within qcut (rare) redo the pass with sqrt_rn
         const unsigned n1 = __ballot_sync(FULL, q1 <= qcut) & gmask, n2 = __ballot_sync(FULL, q2 <= qcut) & gmask;
         const bool tie = __popc(n1) + __popc(n2) > 1;
@@ -226,11 +240,12 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
                 const float q = __fmaf_rn(ey, ey, xmul(ex, ex));
                 if (q <= qcut && __fsqrt_rn(q) == smin) { first = j; break; }
             }
-            const int f2 = (int)__reduce_min_sync(gmask, (unsigned)first);
+            const int f2 = (int)group_min_u32((unsigned)first);
             if (tie) idx = f2;
         }
     }
 
+    GLG_MARK(3);
     __syncwarp();                        // (P <= 2) the centre points become the wall lists from here on
 
     // ---- scan: preconditions, ray table, stage 1 over all vertices ----
@@ -257,6 +272,7 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
     const float Kn = scan_on ? 9.f * EPS_PERP * 1.4143f * 1.001f : 0.f;
     const int passes = (V + PK_G - 1) / PK_G;                              // <= 32 (the host routes N > 256 elsewhere)
     unsigned sbits = 0, fbits = 0, cbits = 0;
+    GLG_MARK(4);
 #pragma unroll PK_S1_UNROLL
     for (int pass = 0; pass < passes; ++pass) {
         const float2 pt = tv.line[pass * PK_G + gl];
@@ -281,6 +297,7 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
         fbits = __brev(fbits) >> sh;
         cbits = __brev(cbits) >> sh;
     }
+    GLG_MARK(5);
     if (!scan_on) { fbits = 0; sbits = 0; }                                // (Kn = close2 = 0 can still flag |im9| < 0: never; belt and braces)
     if (!col_on) cbits = 0;
     unsigned s1 = __shfl_down_sync(FULL, sbits, 1, PK_G), f1 = __shfl_down_sync(FULL, fbits, 1, PK_G);
@@ -331,6 +348,7 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
     }
     __syncwarp();
 
+    GLG_MARK(6);
     // ---- collision: exact test of the walls near the path (race.py:406) ----
     bool wall_hit = false;
     {
@@ -357,6 +375,49 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
     }
     __syncwarp();                        // cq is reused as the candidate queue from here on
 
+    GLG_MARK(7);
+    // ---- finish line, reward, score, state write-back (race.py:431-456) ----
+    if (upd) {
+        const bool dead = wall_hit;
+        const float2 fl = tv.line[2 * N - 1], fr = tv.line[0];             // finish: left[N-1] -> right[N-1], race.py:169
+        bool done = false;
+        {
+            const float x0 = fminf(op.x, np.x) - BOX_MARGIN, x1 = fmaxf(op.x, np.x) + BOX_MARGIN;
+            const float y0 = fminf(op.y, np.y) - BOX_MARGIN, y1 = fmaxf(op.y, np.y) + BOX_MARGIN;
+            const bool apart = fmaxf(fl.x, fr.x) < x0 || fminf(fl.x, fr.x) > x1 ||
+                               fmaxf(fl.y, fr.y) < y0 || fminf(fl.y, fr.y) > y1;
+            if (!apart) done = segments_cross(P2{fl.x, fl.y}, P2{fr.x, fr.y}, op, np);   // race.py:431-432
+        }
+        reward = xadd(reward, xsub(done ? 1.f : 0.f, dead ? 1.f : 0.f));   // race.py:434
+        alive = alive && !dead && !done;                                   // race.py:414, 435
+        fin = fin || done;                                                 // race.py:436
+        if (gl == 0 && (dead || done)) {
+            int sc = __ldcg(&a.st.scores[k]);
+            if (dead) sc = idx + pr.steps_limit + 1;                       // race.py:442-444
+            if (done) sc = step_no;                                        // race.py:446-447
+            a.st.scores[k] = sc;
+        }
+    }
+    if (!alive) nv = 0.f;                                                  // race.py:449
+    const float drag = xsub(1.f, xmul(xsub(1.f, ft != 0 ? 1.f : 0.f), pr.drag));   // race.py:452
+    const float speed = xmul(nv, drag);                                    // race.py:455
+    if (car_on && gl == 0) {
+        reinterpret_cast<float2*>(a.st.directions)[k] = make_float2(nd.x, nd.y);
+        reinterpret_cast<float2*>(a.st.positions)[k] = make_float2(np.x, np.y);
+        a.st.speeds[k] = speed;
+        a.st.alive[k] = alive ? 1 : 0;
+        a.st.finishes[k] = fin ? 1 : 0;
+        a.rewards_out[(size_t)p * B + b] = reward;
+        if (a.history && b == a.record_id) {                               // race.py:492-494
+            float* h = a.history + ((size_t)step_no * P + p) * 6;
+            h[0] = np.x; h[1] = np.y; h[2] = nd.x; h[3] = nd.y; h[4] = (float)act; h[5] = alive ? 1.f : 0.f;
+        }
+        if (a.chain && a.early)
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(a.chain + k), "r"(seq) : "memory");
+        if (alive && a.alive_stamp) atomicMax(&a.alive_stamp[b % GLG_ALIVE_SLOTS], seq);   // (after the release: not waited for)
+    }
+
+    GLG_MARK(8);
     // ---- stage 2: candidate rays of the flagged walls -> queue ----
     int total = 0;
     bool overflow = false;
@@ -395,47 +456,7 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
         }
     }
 
-    // ---- finish line, reward, score, state write-back (race.py:431-456) ----
-    if (upd) {
-        const bool dead = wall_hit;
-        const float2 fl = tv.line[2 * N - 1], fr = tv.line[0];             // finish: left[N-1] -> right[N-1], race.py:169
-        bool done = false;
-        {
-            const float x0 = fminf(op.x, np.x) - BOX_MARGIN, x1 = fmaxf(op.x, np.x) + BOX_MARGIN;
-            const float y0 = fminf(op.y, np.y) - BOX_MARGIN, y1 = fmaxf(op.y, np.y) + BOX_MARGIN;
-            const bool apart = fmaxf(fl.x, fr.x) < x0 || fminf(fl.x, fr.x) > x1 ||
-                               fmaxf(fl.y, fr.y) < y0 || fminf(fl.y, fr.y) > y1;
-            if (!apart) done = segments_cross(P2{fl.x, fl.y}, P2{fr.x, fr.y}, op, np);   // race.py:431-432
-        }
-        reward = xadd(reward, xsub(done ? 1.f : 0.f, dead ? 1.f : 0.f));   // race.py:434
-        alive = alive && !dead && !done;                                   // race.py:414, 435
-        fin = fin || done;                                                 // race.py:436
-        if (gl == 0 && (dead || done)) {
-            int sc = __ldcg(&a.st.scores[k]);
-            if (dead) sc = idx + pr.steps_limit + 1;                       // race.py:442-444
-            if (done) sc = step_no;                                        // race.py:446-447
-            a.st.scores[k] = sc;
-        }
-    }
-    if (!alive) nv = 0.f;                                                  // race.py:449
-    const float drag = xsub(1.f, xmul(xsub(1.f, ft != 0 ? 1.f : 0.f), pr.drag));   // race.py:452
-    const float speed = xmul(nv, drag);                                    // race.py:455
-    if (car_on && gl == 0) {
-        reinterpret_cast<float2*>(a.st.directions)[k] = make_float2(nd.x, nd.y);
-        reinterpret_cast<float2*>(a.st.positions)[k] = make_float2(np.x, np.y);
-        a.st.speeds[k] = speed;
-        a.st.alive[k] = alive ? 1 : 0;
-        a.st.finishes[k] = fin ? 1 : 0;
-        a.rewards_out[(size_t)p * B + b] = reward;
-        if (alive && a.alive_stamp) atomicMax(&a.alive_stamp[b % GLG_ALIVE_SLOTS], seq);
-        if (a.history && b == a.record_id) {                               // race.py:492-494
-            float* h = a.history + ((size_t)step_no * P + p) * 6;
-            h[0] = np.x; h[1] = np.y; h[2] = nd.x; h[3] = nd.y; h[4] = (float)act; h[5] = alive ? 1.f : 0.f;
-        }
-        if (a.chain && a.early)
-            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(a.chain + k), "r"(seq) : "memory");
-    }
-
+    GLG_MARK(9);
     // ---- exact evaluation of the candidates (race.py:287-308), brute force where the pruning did not apply ----
     __syncwarp();
     if (alive && safe && !overflow) {
@@ -454,6 +475,7 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
     if (__any_sync(FULL, brute_s)) packed_sensors_brute(tv, pr, np, nd, gl, gmask, brute_s, car);
     __syncwarp();
 
+    GLG_MARK(10);
     // ---- observation pack [P,B,O+2] (race.py:496-500): 16 lanes write 20 values in two rounds ----
     if (car_on) {
         float* out = a.states_out + ((size_t)p * B + b) * (O + 2);
@@ -476,6 +498,7 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
             }
         }
     }
+    GLG_MARK(11);
     if (a.chain && !a.early) {           // publish "this car's step `seq` is complete" (all lanes' stores first)
         __syncwarp();
         if (car_on && gl == 0) {

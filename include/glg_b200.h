@@ -28,7 +28,8 @@ extern "C" {
 
 #define GLG_MAX_PLAYERS   8
 #define GLG_MAX_RAYS      32
-#define GLG_ALIVE_SLOTS   64  /* int32 slots of the "somebody is alive" step stamp            */
+#define GLG_ALIVE_SLOTS   1024 /* int32 slots of the "somebody is alive" step stamp (many, so that
+                                 the atomic max of a launch does not pile up on a few addresses)  */
 
 /* step kernel variants (all produce identical results; tests compare them) */
 #define GLG_STEP_FAST     0   /* two-stage exact pruning of the ray cast, one warp per car (18 rays) */
@@ -132,7 +133,7 @@ int glg_race_init(glg_race_state state, int32_t B, int32_t P, int32_t* alive_sta
  *   extent     [B,2] f32 from glg_track_extent (required by GLG_STEP_PACKED / FAST, else may be NULL)
  *   step_no    value of Race.steps AFTER the increment of this step (race.py:349)
  *   states_out [P,B,num_rays+2] f32, rewards_out [P,B] f32
- *   alive_stamp [GLG_ALIVE_SLOTS] i32 or NULL: slot (b % 64) := max(slot, launch_seq) if track b still
+ *   alive_stamp [GLG_ALIVE_SLOTS] i32 or NULL: slot (b % GLG_ALIVE_SLOTS) := max(slot, launch_seq) if track b still
  *              has an alive car after this step (host reads it for Race.finished(), race.py:502-504)
  *   launch_seq a number the caller increases with every launch on this environment (> 0)
  *   base       NULL, or a device pointer to {step_no offset, launch_seq offset} (2 x i32) that the kernel adds to

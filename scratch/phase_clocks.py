@@ -12,9 +12,10 @@ h.glg_debug_phases(buf, 1)
 n = 20
 for _ in range(n): rep.cycle(100)
 h.glg_debug_phases(buf, 1)
-warps = n * 100 * bench.B_TRACKS * bench.P_CARS
-names = {0: 'launch..griddep wait', 1: 'state loads + kinematics', 2: 'syncthreads + TMA wait', 3: 'progress arg-min', 5: 'scan pre + stage 1', 6: 'lists', 7: 'collision', 8: 'stage 2 + emit', 9: 'reward/finish (rest of main between 3 and 9 minus scan)', 10: 'flush (exact eval)', 11: 'state write + (sensors_finish rest)', 12: 'pack'}
+warps = n * 100 * bench.B_TRACKS
+names = {0: 'launch, TMA issue, chain/grid wait', 1: 'state loads + kinematics', 2: 'barrier + TMA wait', 3: 'progress arg-min', 4: 'scan pre + ray table', 5: 'stage 1', 6: 'lists', 7: 'collision', 8: 'finish/reward/write-back/release', 9: 'stage 2 + emit', 10: 'exact evaluation', 11: 'pack'}
+old_names = {0: 'launch..griddep wait', 1: 'state loads + kinematics', 2: 'syncthreads + TMA wait', 3: 'progress arg-min', 5: 'scan pre + stage 1', 6: 'lists', 7: 'collision', 8: 'stage 2 + emit', 9: 'reward/finish (rest of main between 3 and 9 minus scan)', 10: 'flush (exact eval)', 11: 'state write + (sensors_finish rest)', 12: 'pack'}
 tot = sum(buf[i] for i in range(32))
 for i in range(32):
     if buf[i]: print('%2d %-55s %8.0f cycles/warp %5.1f%%' % (i, names.get(i, ''), buf[i] / warps, 100. * buf[i] / tot))
-print('sum', tot / warps, '(note: marks 5-8 and 10 are nested inside 9 and 11)')
+print('sum', tot / warps)
