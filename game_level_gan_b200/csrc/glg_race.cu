@@ -40,6 +40,8 @@ struct StepArgs {
     int32_t chained;      // wait for chain[car] == seq-1 instead of for the whole previous grid
     int32_t early;        // publish chain[car] right after the state write-back (outputs of different steps do not alias)
     PackedLayout pk;      // filled by launch_packed
+    unsigned long long* ll;                  // [B*P][6] LL hand-over words (packed kernel, glg_race_packed.cuh)
+    int32_t ll_read, ll_write, arrays_write;
 };
 
 __global__ void race_init_kernel(glg_race_state st, int K, int32_t* alive_stamp)
@@ -386,6 +388,17 @@ static void launch_one(const glg_race_params* pr, const StepArgs& a, cudaStream_
     cudaLaunchKernelEx(&cfg, race_step_kernel<VARIANT, OC>, *pr, a);
 }
 
+// the variant that actually runs (PACKED covers 18 rays, N <= 256 and 16-byte granular records = even N)
+static int effective_variant(const glg_race_params* pr, const float* geom, int N, int variant)
+{
+    if (variant == GLG_STEP_PACKED && (pr->num_rays != 18 || N > 256 || (N & 1) || ((uintptr_t)geom & 15u)))
+        variant = GLG_STEP_FAST;
+    if (variant == GLG_STEP_FAST && pr->num_rays != 18) variant = GLG_STEP_SCAN;    // stage 1 is written for 9 ray lines
+    if (variant == GLG_STEP_SCAN && (pr->num_rays & 1)) variant = GLG_STEP_BRUTE;   // pruning pairs opposite rays
+    if (variant == GLG_STEP_SCAN && (2 * N - 1 + 30) / 31 > 32) variant = GLG_STEP_BRUTE;   // 32-bit pass bitmap
+    return variant;
+}
+
 template <int TPB>
 static void launch_packed(const glg_race_params* pr, const StepArgs& a, cudaStream_t stream)
 {
@@ -418,18 +431,12 @@ static void launch_packed(const glg_race_params* pr, const StepArgs& a, cudaStre
 
 static int launch_step(const glg_race_params* pr, const StepArgs& a, int variant, cudaStream_t stream)
 {
-    // PACKED (two cars per warp) is written for 18 rays and at most 32 half-warp passes over the polyline
-    // (and stages the record with a bulk copy: 16-byte granular records only, i.e. even N)
-    if (variant == GLG_STEP_PACKED && (pr->num_rays != 18 || a.N > 256 || (a.N & 1) || ((uintptr_t)a.geom & 15u)))
-        variant = GLG_STEP_FAST;
+    variant = effective_variant(pr, a.geom, a.N, variant);
     if (variant == GLG_STEP_PACKED) {
         if (pr->num_players <= 2) launch_packed<2>(pr, a, stream);
         else launch_packed<1>(pr, a, stream);
         return GLG_OK;
     }
-    if (variant == GLG_STEP_FAST && pr->num_rays != 18) variant = GLG_STEP_SCAN;    // stage 1 is written for 9 ray lines
-    if (variant == GLG_STEP_SCAN && (pr->num_rays & 1)) variant = GLG_STEP_BRUTE;   // pruning pairs opposite rays
-    if (variant == GLG_STEP_SCAN && (2 * a.N - 1 + 30) / 31 > 32) variant = GLG_STEP_BRUTE;   // 32-bit pass bitmap
     if (variant == GLG_STEP_BRUTE) launch_one<GLG_STEP_BRUTE, 0>(pr, a, stream);
     else if (variant == GLG_STEP_FAST) launch_one<GLG_STEP_FAST, 18>(pr, a, stream);
     else if (pr->num_rays == 18) launch_one<GLG_STEP_SCAN, 18>(pr, a, stream);
@@ -477,7 +484,7 @@ extern "C" int glg_race_step(const glg_race_params* params, const float* geom, i
     const int rc = check_step_args(params, geom, B, N, actions, valid, extent, variant, state, states_out, rewards_out);
     if (rc != GLG_OK || B == 0) return rc;
     StepArgs a{geom, actions, valid, extent, state, states_out, rewards_out, alive_stamp, history, nullptr, base,
-               B, N, step_no, record_id, launch_seq, 0, 0, {}};
+               B, N, step_no, record_id, launch_seq, 0, 0, {}, nullptr, 0, 0, 1};
     launch_step(params, a, variant, (cudaStream_t)stream);
     return launch_status("glg_race_step");
 }
@@ -494,15 +501,25 @@ extern "C" int glg_race_rollout(const glg_race_params* params, const float* geom
     if (rc != GLG_OK || B == 0 || T <= 0) return rc;
     const size_t PB = (size_t)params->num_players * B;
     const size_t W = params->num_rays + 2;
+    // LL hand-over (packed kernel, every step has its own output buffer): see glg_race_packed.cuh
+    const bool ll = chain != nullptr && keep_all && effective_variant(params, geom, N, variant) == GLG_STEP_PACKED;
+    unsigned long long* llw = chain ? reinterpret_cast<unsigned long long*>(chain + ((PB + 3) & ~(size_t)3)) : nullptr;
     for (int t = 0; t < T; ++t) {
         StepArgs a{geom, actions + (size_t)t * PB, valid, extent, state,
                    keep_all ? states_out + (size_t)t * PB * W : states_out,
                    keep_all ? rewards_out + (size_t)t * PB : rewards_out,
                    alive_stamp, nullptr, chain, nullptr, B, N, first_step_no + t, -1, first_launch_seq + t,
-                   (chain != nullptr && t > 0) ? 1 : 0, keep_all ? 1 : 0, {}};
+                   (chain != nullptr && t > 0) ? 1 : 0, keep_all ? 1 : 0, {}, llw,
+                   (ll && t > 0) ? 1 : 0, (ll && t < T - 1) ? 1 : 0, (!ll || t == T - 1) ? 1 : 0};
         launch_step(params, a, variant, (cudaStream_t)stream);
     }
     return launch_status("glg_race_rollout");
+}
+
+extern "C" int64_t glg_race_chain_bytes(int32_t B, int32_t P)
+{
+    const int64_t cars = (int64_t)B * P;
+    return (((cars + 3) & ~(int64_t)3) + 12 * cars) * (int64_t)sizeof(int32_t);
 }
 
 extern "C" int glg_race_winners(const int32_t* scores, const uint8_t* finishes, const uint8_t* valid,

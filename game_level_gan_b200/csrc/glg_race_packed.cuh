@@ -161,7 +161,26 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
         record_copy_async(pts, reinterpret_cast<const float2*>(a.geom) + (size_t)b * 3 * N, rec_bytes, bar);
     asm volatile("griddepcontrol.launch_dependents;");
     const int k = b * P + p;
-    if (a.chained) {
+    // "LL" chaining (rollouts that keep every step's outputs): the previous step of this car hands its state
+    // over in six 64-bit words {launch number : value} - single-copy atomic, self-validating, so neither side
+    // needs a fence and the consumer needs no second round trip for the state itself.
+    unsigned llw = 0;
+    if (a.ll_read) {
+        if (car_on && gl < 6) {
+            const unsigned want = (unsigned)(seq - 1);
+            const unsigned long long* w = a.ll + (size_t)k * 6 + gl;
+            unsigned long long x;
+            int spin = 0;
+            do {
+                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(x) : "l"(w) : "memory");
+                if ((unsigned)(x >> 32) == want) break;
+                __nanosleep(GLG_CHAIN_BACKOFF_NS);
+                if (++spin > (1 << 22)) __trap();
+            } while (true);
+            llw = (unsigned)x;
+        }
+        __syncwarp();
+    } else if (a.chained) {
         if (car_on && gl == 0) {
             const int want = seq - 1;
             int got, spin = 0;
@@ -184,14 +203,28 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
     float2 dir = make_float2(0.f, 1.f), pos = make_float2(0.f, 0.f);
     float spd = 0.f;
     float2 ext = make_float2(INF, INF);
+    if (a.ll_read) {                     // words: pos.x, pos.y, dir.x, dir.y, speed, flags (alive | finished << 1)
+        pos.x = __uint_as_float(__shfl_sync(FULL, llw, 0, PK_G));
+        pos.y = __uint_as_float(__shfl_sync(FULL, llw, 1, PK_G));
+        dir.x = __uint_as_float(__shfl_sync(FULL, llw, 2, PK_G));
+        dir.y = __uint_as_float(__shfl_sync(FULL, llw, 3, PK_G));
+        spd = __uint_as_float(__shfl_sync(FULL, llw, 4, PK_G));
+        const unsigned fl = __shfl_sync(FULL, llw, 5, PK_G);
+        if (car_on) {
+            alive = (fl & 1u) != 0u;
+            fin = (fl & 2u) != 0u;
+        }
+    }
     if (car_on) {
-        alive = __ldcg(&a.st.alive[k]) != 0;
-        fin = __ldcg(&a.st.finishes[k]) != 0;
+        if (!a.ll_read) {
+            alive = __ldcg(&a.st.alive[k]) != 0;
+            fin = __ldcg(&a.st.finishes[k]) != 0;
+            dir = __ldcg(reinterpret_cast<const float2*>(a.st.directions) + k);
+            pos = __ldcg(reinterpret_cast<const float2*>(a.st.positions) + k);
+            spd = __ldcg(&a.st.speeds[k]);
+        }
         ok = a.valid[b] != 0;
         act = (int)a.actions[(size_t)p * B + b];
-        dir = __ldcg(reinterpret_cast<const float2*>(a.st.directions) + k);
-        pos = __ldcg(reinterpret_cast<const float2*>(a.st.positions) + k);
-        spd = __ldcg(&a.st.speeds[k]);
         ext = __ldg(reinterpret_cast<const float2*>(a.extent) + b);
     }
     const int pc = min(p, GLG_MAX_PLAYERS - 1);
@@ -391,28 +424,33 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
         reward = xadd(reward, xsub(done ? 1.f : 0.f, dead ? 1.f : 0.f));   // race.py:434
         alive = alive && !dead && !done;                                   // race.py:414, 435
         fin = fin || done;                                                 // race.py:436
-        if (gl == 0 && (dead || done)) {
-            int sc = __ldcg(&a.st.scores[k]);
-            if (dead) sc = idx + pr.steps_limit + 1;                       // race.py:442-444
-            if (done) sc = step_no;                                        // race.py:446-447
-            a.st.scores[k] = sc;
-        }
+        if (gl == 0 && (dead || done))                                     // race.py:442-447 (done wins over dead)
+            a.st.scores[k] = done ? step_no : idx + pr.steps_limit + 1;
     }
     if (!alive) nv = 0.f;                                                  // race.py:449
     const float drag = xsub(1.f, xmul(xsub(1.f, ft != 0 ? 1.f : 0.f), pr.drag));   // race.py:452
     const float speed = xmul(nv, drag);                                    // race.py:455
+    if (a.ll_write && car_on && gl < 6) {
+        const unsigned word = gl == 0 ? __float_as_uint(np.x) : gl == 1 ? __float_as_uint(np.y)
+                            : gl == 2 ? __float_as_uint(nd.x) : gl == 3 ? __float_as_uint(nd.y)
+                            : gl == 4 ? __float_as_uint(speed) : ((alive ? 1u : 0u) | (fin ? 2u : 0u));
+        const unsigned long long x = ((unsigned long long)(unsigned)seq << 32) | word;
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(a.ll + (size_t)k * 6 + gl), "l"(x) : "memory");
+    }
     if (car_on && gl == 0) {
-        reinterpret_cast<float2*>(a.st.directions)[k] = make_float2(nd.x, nd.y);
-        reinterpret_cast<float2*>(a.st.positions)[k] = make_float2(np.x, np.y);
-        a.st.speeds[k] = speed;
-        a.st.alive[k] = alive ? 1 : 0;
-        a.st.finishes[k] = fin ? 1 : 0;
+        if (a.arrays_write) {            // (intermediate launches of an LL rollout hand the state over in the LL words only)
+            reinterpret_cast<float2*>(a.st.directions)[k] = make_float2(nd.x, nd.y);
+            reinterpret_cast<float2*>(a.st.positions)[k] = make_float2(np.x, np.y);
+            a.st.speeds[k] = speed;
+            a.st.alive[k] = alive ? 1 : 0;
+            a.st.finishes[k] = fin ? 1 : 0;
+        }
         a.rewards_out[(size_t)p * B + b] = reward;
         if (a.history && b == a.record_id) {                               // race.py:492-494
             float* h = a.history + ((size_t)step_no * P + p) * 6;
             h[0] = np.x; h[1] = np.y; h[2] = nd.x; h[3] = nd.y; h[4] = (float)act; h[5] = alive ? 1.f : 0.f;
         }
-        if (a.chain && a.early)
+        if (a.chain && a.early && !a.ll_write)
             asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(a.chain + k), "r"(seq) : "memory");
         if (alive && a.alive_stamp) atomicMax(&a.alive_stamp[b % GLG_ALIVE_SLOTS], seq);   // (after the release: not waited for)
     }
@@ -499,7 +537,7 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
         }
     }
     GLG_MARK(11);
-    if (a.chain && !a.early) {           // publish "this car's step `seq` is complete" (all lanes' stores first)
+    if (a.chain && !a.early && !a.ll_write) {   // publish "this car's step `seq` is complete" (all lanes' stores first)
         __syncwarp();
         if (car_on && gl == 0) {
             __threadfence();

@@ -191,7 +191,8 @@ class Race(MultiEnvironment):
             self.scores = torch.empty((B, P), dtype=torch.int32, device=dev)
             self._stamp = torch.empty((_lib.ALIVE_SLOTS,), dtype=torch.int32, device=dev)
             self._stamp_host = torch.zeros((_lib.ALIVE_SLOTS,), dtype=torch.int32).pin_memory()
-            self._chain = torch.zeros((B, P), dtype=torch.int32, device=dev)      # per-car launch stamps (rollout)
+            self._chain = torch.zeros((max(int(lib.glg_race_chain_bytes(B, P)) // 4, 4),), dtype=torch.int32,
+                                      device=dev)                                  # per-car stamps / hand-over words (rollout)
             self._seq = 0                                                         # launch sequence number
             self._state = RaceState(ptr(self.positions), ptr(self.directions), ptr(self.speeds),
                                     ptr(self._alive), ptr(self._finishes), ptr(self.scores))

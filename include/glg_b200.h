@@ -153,17 +153,22 @@ int glg_race_step(const glg_race_params* params, const float* geom, int32_t B, i
  * Launches T step kernels back to back on `stream`; states_out/rewards_out hold the LAST step's
  * outputs, or all steps if `keep_all` (then [T,P,B,W] / [T,P,B]).  first_step_no as in glg_race_step;
  * launch t uses launch_seq = first_launch_seq + t.
- *   chain  [B,P] i32 scratch or NULL.  With it, launches 1..T-1 do not wait for the whole previous grid but,
+ *   chain  scratch of glg_race_chain_bytes(B, P) bytes (16-byte aligned, zero-filled once) or NULL.  With it, launches 1..T-1 do not wait for the whole previous grid but,
  *          warp by warp, for the previous step of their own car (chain[car] == launch_seq - 1, published with
  *          release/acquire), so consecutive steps overlap; results are identical.  With keep_all the stamp is
  *          published right after the car state is written back (before the ray cast), without it after the
- *          outputs (the steps share one output buffer).  The numbers
+ *          outputs (the steps share one output buffer).  The production kernel with keep_all goes one step
+ *          further: the car state travels from launch to launch in six self-validating 64-bit words
+ *          {launch number : value} of `chain` (no fences, no second round trip) and only the last launch
+ *          writes the state arrays.  The numbers
  *          first_launch_seq .. first_launch_seq+T-1 must be larger than anything stored in `chain` before. */
 int glg_race_rollout(const glg_race_params* params, const float* geom, int32_t B, int32_t N,
                      const int64_t* actions, int32_t T, const uint8_t* valid, const float* extent,
                      glg_race_state state, int32_t first_step_no, float* states_out, float* rewards_out, int32_t keep_all,
                      int32_t* alive_stamp, int32_t first_launch_seq, int32_t* chain,
                      int32_t variant, glg_stream_t stream);
+
+int64_t glg_race_chain_bytes(int32_t B, int32_t P);
 
 /* Winner per track.  Replaces Race.winners, games/race.py:506-529.  winners [B] i64 out.      */
 int glg_race_winners(const int32_t* scores, const uint8_t* finishes, const uint8_t* valid,
