@@ -251,12 +251,29 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
     {
         float q1 = INF, q2 = INF;
         int j1 = 0x7fffffff;
-        for (int j = gl; j < N; j += PK_G) {
-            const float2 cpt = tv.centre[j];
-            const float ex = xsub(np.x, cpt.x), ey = xsub(np.y, cpt.y);
-            const float q = __fmaf_rn(ey, ey, xmul(ex, ex));
-            if (q < q1) { q2 = q1; q1 = q; j1 = j; }
-            else q2 = fminf(q2, q);
+        {
+            const float2* cp = tv.centre + gl;
+            const int full = N / PK_G;                         // iterations in which every lane has a point
+            int j = gl;
+#pragma unroll 3
+            for (int it = 0; it < full; ++it, cp += PK_G, j += PK_G) {
+                const float2 cpt = *cp;
+                const float ex = xsub(np.x, cpt.x), ey = xsub(np.y, cpt.y);
+                const float q = __fmaf_rn(ey, ey, xmul(ex, ex));
+                const bool less = q < q1;
+                q2 = less ? q1 : fminf(q2, q);
+                j1 = less ? j : j1;
+                q1 = less ? q : q1;
+            }
+            if (j < N) {                                       // tail
+                const float2 cpt = *cp;
+                const float ex = xsub(np.x, cpt.x), ey = xsub(np.y, cpt.y);
+                const float q = __fmaf_rn(ey, ey, xmul(ex, ex));
+                const bool less = q < q1;
+                q2 = less ? q1 : fminf(q2, q);
+                j1 = less ? j : j1;
+                q1 = less ? q : q1;
+            }
         }
         const float qmin = __uint_as_float(group_min_u32(__float_as_uint(q1)));              // q >= 0
         const float qcut = qmin * 1.000001f + 1e-45f;
@@ -288,11 +305,16 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
     const bool safe = d2 > 0.5f && d2 < 2.f && fabsf(np.x) + fabsf(np.y) + ext.x < 200.f;   // see scan_two_stage
     const bool scan_on = alive && safe;
     if (gl < 2) car->tmin[PK_RAYS + gl] = 0;
-    for (int i = gl; i < O; i += PK_G) {
+    {                                    // 18 rays, 16 lanes: lanes 0..15 take ray gl, lanes 0 and 1 also rays 16 and 17
         P2 d, f;
-        ray_setup(pr, i, np, nd, d, f);
-        car->ray[i] = make_float4(d.x, d.y, f.x, f.y);
-        car->tmin[i] = 0x7f800000;
+        ray_setup(pr, gl, np, nd, d, f);
+        car->ray[gl] = make_float4(d.x, d.y, f.x, f.y);
+        car->tmin[gl] = 0x7f800000;
+        if (gl < O - PK_G) {
+            ray_setup(pr, PK_G + gl, np, nd, d, f);
+            car->ray[PK_G + gl] = make_float4(d.x, d.y, f.x, f.y);
+            car->tmin[PK_G + gl] = 0x7f800000;
+        }
     }
     if (gl == 0) car->nan_mask = 0;
 
@@ -306,23 +328,46 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
     const int passes = (V + PK_G - 1) / PK_G;                              // <= 32 (the host routes N > 256 elsewhere)
     unsigned sbits = 0, fbits = 0, cbits = 0;
     GLG_MARK(4);
-#pragma unroll PK_S1_UNROLL
-    for (int pass = 0; pass < passes; ++pass) {
-        const float2 pt = tv.line[pass * PK_G + gl];
-        const float ux = pt.x - np.x, uy = pt.y - np.y;
-        const float za = fmaf(ux, nd.x, uy * nd.y);
-        const float zb = fmaf(ux, nd.y, -(uy * nd.x));
-        const float a2 = za * za, b2 = zb * zb;
-        const float r2z = a2 + b2;
-        const float re3 = za * fmaf(-3.f, b2, a2);
-        const float im3 = zb * fmaf(3.f, a2, -b2);
-        const float im9 = im3 * fmaf(3.f, re3 * re3, -(im3 * im3));
-        const float r4 = r2z * r2z;
-        const float near = fmaf(r4 * r4, -Kn, fabsf(im9));
-        const float flag = fminf(near, r2z - close2);
-        sbits = __funnelshift_l(__float_as_uint(im9), sbits, 1);
-        fbits = __funnelshift_l(__float_as_uint(flag), fbits, 1);
-        cbits = __funnelshift_l(__float_as_uint(r2z - col2), cbits, 1);
+    {
+        const float2* vp = tv.line + gl;
+        const int quads = passes >> 2;
+        for (int it = 0; it < quads; ++it, vp += 4 * PK_G) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float2 pt = vp[u * PK_G];
+                const float ux = pt.x - np.x, uy = pt.y - np.y;
+                const float za = fmaf(ux, nd.x, uy * nd.y);
+                const float zb = fmaf(ux, nd.y, -(uy * nd.x));
+                const float a2 = za * za, b2 = zb * zb;
+                const float r2z = a2 + b2;
+                const float re3 = za * fmaf(-3.f, b2, a2);
+                const float im3 = zb * fmaf(3.f, a2, -b2);
+                const float im9 = im3 * fmaf(3.f, re3 * re3, -(im3 * im3));
+                const float r4 = r2z * r2z;
+                const float near = fmaf(r4 * r4, -Kn, fabsf(im9));
+                const float flag = fminf(near, r2z - close2);
+                sbits = __funnelshift_l(__float_as_uint(im9), sbits, 1);
+                fbits = __funnelshift_l(__float_as_uint(flag), fbits, 1);
+                cbits = __funnelshift_l(__float_as_uint(r2z - col2), cbits, 1);
+            }
+        }
+        for (int it = passes & 3; it > 0; --it, vp += PK_G) {
+            const float2 pt = *vp;
+            const float ux = pt.x - np.x, uy = pt.y - np.y;
+            const float za = fmaf(ux, nd.x, uy * nd.y);
+            const float zb = fmaf(ux, nd.y, -(uy * nd.x));
+            const float a2 = za * za, b2 = zb * zb;
+            const float r2z = a2 + b2;
+            const float re3 = za * fmaf(-3.f, b2, a2);
+            const float im3 = zb * fmaf(3.f, a2, -b2);
+            const float im9 = im3 * fmaf(3.f, re3 * re3, -(im3 * im3));
+            const float r4 = r2z * r2z;
+            const float near = fmaf(r4 * r4, -Kn, fabsf(im9));
+            const float flag = fminf(near, r2z - close2);
+            sbits = __funnelshift_l(__float_as_uint(im9), sbits, 1);
+            fbits = __funnelshift_l(__float_as_uint(flag), fbits, 1);
+            cbits = __funnelshift_l(__float_as_uint(r2z - col2), cbits, 1);
+        }
     }
     {
         const int sh = 32 - passes;
@@ -352,6 +397,14 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
         }
         nw = __shfl_sync(FULL, incl, PK_G - 1, PK_G);
         int posn = incl - cnt;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {                                      // straight-line for the usual <= 3 walls per lane
+            if (wbits) {
+                const int pass = __ffs(wbits) - 1;
+                wbits &= wbits - 1;
+                wlist[posn++] = (unsigned short)(pass * PK_G + gl);
+            }
+        }
         while (wbits) {
             const int pass = __ffs(wbits) - 1;
             wbits &= wbits - 1;
@@ -484,10 +537,19 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
             if (total + tot > PK_QCAP) overflow = true;
             if (!overflow) {
                 int posn = total + incl - cnt;
+                const int wcode = w << 5;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {                              // straight-line for the usual <= 2 rays per wall
+                    if (mask) {
+                        const int i = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        cq[posn++] = (unsigned short)(wcode | i);
+                    }
+                }
                 while (mask) {
                     const int i = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    cq[posn++] = (unsigned short)((w << 5) | i);
+                    cq[posn++] = (unsigned short)(wcode | i);
                 }
                 total += tot;
             }
