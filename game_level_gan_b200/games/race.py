@@ -197,6 +197,9 @@ class Race(MultiEnvironment):
             self._state = RaceState(ptr(self.positions), ptr(self.directions), ptr(self.speeds),
                                     ptr(self._alive), ptr(self._finishes), ptr(self.scores))
             check(lib.glg_race_init(self._state, B, P, ptr(self._stamp), stream), 'glg_race_init')
+            self._stamp_np = self._stamp_host.numpy()      # same memory; numpy compares are cheaper per step
+            self._step_const = (lib.glg_race_step, ptr(self._geom), N, ptr(self._valid_tracks), ptr(self._extent),
+                                ptr(self._stamp))
             self._alive_known = B * P > 0
             self._hist_steps = []
             self._hist = None
@@ -211,10 +214,12 @@ class Race(MultiEnvironment):
         dev = self.device
         with torch.no_grad():
             B, P, O = self.num_tracks, self.num_players, self.observation_size
-            actions = actions.detach().to(device=dev, dtype=torch.int64).contiguous()
+            if not (actions.dtype == torch.int64 and actions.device == dev and actions.is_contiguous()):
+                actions = actions.detach().to(device=dev, dtype=torch.int64).contiguous()
             if tuple(actions.shape) != (P, B):
                 raise ValueError('actions must have shape [num_players, num_boards] = [%d, %d]' % (P, B))
-            anybody_alive = self._any_alive()              # state after the previous step
+            stream = torch.cuda.current_stream(dev)
+            anybody_alive = self._any_alive(stream)        # state after the previous step
             self.steps += 1
             if not anybody_alive:                          # games/race.py:353-356 (19-wide quirk)
                 states = torch.zeros((P, B, O + 1), dtype=torch.float32, device=dev)
@@ -231,10 +236,12 @@ class Race(MultiEnvironment):
                 hist = self._hist
                 self._hist_steps.append(self.steps)
             self._seq += 1
-            check(_lib.lib().glg_race_step(
-                self._params, ptr(self._geom), B, self._geom.size(2), ptr(actions), ptr(self._valid_tracks),
-                ptr(self._extent), self._state, self.steps, ptr(states), ptr(rewards), ptr(self._stamp), self._seq,
-                None, ptr(hist), self.record_id, self._variant_code(), _lib.stream_ptr(dev)), 'glg_race_step')
+            c = self._step_const                           # pointers that do not change between resets
+            rc = c[0](self._params, c[1], B, c[2], actions.data_ptr(), c[3], c[4], self._state, self.steps,
+                      states.data_ptr(), rewards.data_ptr(), c[5], self._seq, None, ptr(hist), self.record_id,
+                      self._variant_code(), stream.cuda_stream)
+            if rc != 0:
+                check(rc, 'glg_race_step')
             self._alive_known = None
             return states, rewards
 
@@ -288,11 +295,11 @@ class Race(MultiEnvironment):
         self.steps = snap['steps']
         self._alive_known = snap['alive_known']
 
-    def _any_alive(self):
+    def _any_alive(self, stream=None):
         if self._alive_known is None:
             self._stamp_host.copy_(self._stamp, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-            self._alive_known = bool((self._stamp_host == self._seq).any())
+            (stream if stream is not None else torch.cuda.current_stream(self.device)).synchronize()
+            self._alive_known = bool((self._stamp_np == self._seq).any())
         return self._alive_known
 
     def finished(self):
