@@ -102,7 +102,7 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
         asm volatile("griddepcontrol.wait;" ::: "memory");
         step_no += __ldcg(a.base);
         seq += __ldcg(a.base + 1);
-        if (step_no > pr.steps_limit + 1) return;     // past the time limit (Race.finished()): the step is a no-op
+        if (step_no > __ldcg(a.base + 2)) return;     // past the time limit (Race.finished()): the step is a no-op
     }
     GLG_MARK_INIT;
     GLG_TRACE(0);

@@ -5,7 +5,7 @@ from .race import Race, RaceCar
 from .race_utils import RaceConfig, predefined_tracks, race_game
 from .pytorch_wrapper import PytorchWrapper
 from . import game_helpers
-from .rollout import GraphedRollout
+from .rollout import GraphedRollout, HostStepper
 
 __all__ = ['MultiEnvironment', 'Pacman', 'Race', 'RaceCar', 'RaceConfig', 'predefined_tracks', 'race_game',
-           'PytorchWrapper', 'game_helpers', 'GraphedRollout']
+           'PytorchWrapper', 'game_helpers', 'GraphedRollout', 'HostStepper']

@@ -245,15 +245,21 @@ class Race(MultiEnvironment):
             self._alive_known = None
             return states, rewards
 
-    def step_into(self, actions, states_out, rewards_out, base, offset):
+    def step_into(self, actions, states_out, rewards_out, base, offset, stamp=None):
         """Capture-safe step for CUDA graphs (games/rollout.py): no allocation, no host synchronisation, no
         early-out; the step number and launch number are `offset` plus the two int32 counters in the
-        device tensor `base`, and steps past the time limit do nothing (include/glg_b200.h)."""
+        device tensor `base`; steps beyond base[2] do nothing (include/glg_b200.h)."""
         B = self.num_tracks
         check(_lib.lib().glg_race_step(
             self._params, ptr(self._geom), B, self._geom.size(2), ptr(actions), ptr(self._valid_tracks),
-            ptr(self._extent), self._state, offset, ptr(states_out), ptr(rewards_out), ptr(self._stamp), offset,
-            ptr(base), None, -1, self._variant_code(), _lib.stream_ptr(self.device)), 'glg_race_step')
+            ptr(self._extent), self._state, offset, ptr(states_out), ptr(rewards_out),
+            ptr(self._stamp if stamp is None else stamp), offset, ptr(base), None, -1, self._variant_code(), _lib.stream_ptr(self.device)), 'glg_race_step')
+
+    def host_stepper(self):
+        """A `HostStepper` (games/rollout.py) for this episode: `step` with host-resident actions / observations
+        as one CUDA graph per step."""
+        from .rollout import HostStepper
+        return HostStepper(self)
 
     def rollout(self, actions, keep_all=False, chained=True):
         """T steps with pre-computed actions [T,P,B] (no per-step host work).  Returns the outputs of

@@ -9,8 +9,10 @@ the episode has ended change nothing (dead and finished cars are frozen, steps p
 no-ops in the kernel), and `Race.steps` is set to what the reference's loop would have counted, so the
 state of the environment after `run()` is the same as after the reference's loop.
 """
+import numpy as np
 import torch
 
+from .. import _lib
 from .._lib import GlgError
 
 
@@ -28,21 +30,21 @@ class GraphedRollout(object):
         self.states = torch.zeros((P, B, O + 2), dtype=torch.float32, device=dev)
         self.rewards = torch.zeros((P, B), dtype=torch.float32, device=dev)
         self.actions = torch.zeros((P, B), dtype=torch.int64, device=dev)
-        self.base = torch.zeros((2,), dtype=torch.int32, device=dev)      # {step number, launch number} so far
+        self.base = torch.zeros((3,), dtype=torch.int32, device=dev)      # {step number, launch number} so far, last step
         self.graph = None
 
     def _body(self):
         for j in range(1, self.k + 1):
             self.actions.copy_(self.act(self.states))
             self.env.step_into(self.actions, self.states, self.rewards, self.base, j)
-        self.base += self.k
+        self.base[:2] += self.k
 
     def capture(self):
         side = torch.cuda.Stream(device=self.env.device)
         side.wait_stream(torch.cuda.current_stream(self.env.device))
         with torch.cuda.stream(side), torch.no_grad():      # warm-up outside the graph (allocator, lazy init)
             saved = self.env.snapshot(), self.env._chain.clone(), self.env._stamp.clone(), self.states.clone()
-            self.base.copy_(torch.tensor([self.env.steps, self.env._seq], dtype=torch.int32))
+            self.base.copy_(torch.tensor([self.env.steps, self.env._seq, self.env.steps_limit + 1], dtype=torch.int32))
             self._body()
             side.synchronize()
             self.env.restore(saved[0])
@@ -66,7 +68,7 @@ class GraphedRollout(object):
         if self.on_reset is not None:
             self.on_reset()
         start_steps, start_seq = env.steps, env._seq
-        self.base.copy_(torch.tensor([start_steps, start_seq], dtype=torch.int32), non_blocking=True)
+        self.base.copy_(torch.tensor([start_steps, start_seq, env.steps_limit + 1], dtype=torch.int32))
         replays = 0
         while not env.finished() and (max_replays is None or replays < max_replays):
             self.graph.replay()
@@ -84,3 +86,68 @@ class GraphedRollout(object):
             ran = replays * self.k
             env.steps = start_steps + min(ran, by_death, by_time)
         return self.states, self.rewards
+
+
+class HostStepper(object):
+    """`Race.step` for callers whose policies live on the HOST: actions come from and observations go to
+    (pinned) host memory every step.  One CUDA graph holds the whole round trip - H2D of the actions and of the
+    step counters, the step kernel, D2H of observations, rewards and the alive stamp - so a step costs one
+    graph launch and one synchronisation instead of five enqueues.  Same results as `Race.step`, including the
+    "nobody alive" early-out (games/race.py:353-356); the returned tensors are views of pinned buffers that the
+    next call overwrites.
+    """
+
+    def __init__(self, env):
+        if env.num_tracks is None or env.num_tracks == 0:
+            raise GlgError('HostStepper needs a reset environment with at least one track')
+        self.env = env
+        dev = env.device
+        B, P, O = env.num_tracks, env.num_players, env.observation_size
+        # one input block {step counters (16 B) | actions} and one output block {observations | rewards | alive stamp}
+        # on each side, so that the graph is H2D -> step kernel -> D2H
+        n_obs, n_rw = P * B * (O + 2), P * B
+        self.in_h = torch.zeros((2 + P * B,), dtype=torch.int64).pin_memory()
+        self.in_d = torch.zeros((2 + P * B,), dtype=torch.int64, device=dev)
+        self.out_h = torch.zeros((n_obs + n_rw + _lib.ALIVE_SLOTS,), dtype=torch.float32).pin_memory()
+        self.out_d = torch.zeros((n_obs + n_rw + _lib.ALIVE_SLOTS,), dtype=torch.float32, device=dev)
+        self.actions_h = self.in_h[2:].view(P, B)
+        self._actions_np = self.actions_h.numpy()
+        self._base_np = self.in_h[:2].view(torch.int32).numpy()         # {step number, launch number, last step, -}
+        self._base_np[2] = 2 ** 31 - 1                                  # no step limit, like Race.step
+        self.states_h = self.out_h[:n_obs].view(P, B, O + 2)
+        self.rewards_h = self.out_h[n_obs:n_obs + n_rw].view(P, B)
+        self._stamp_np = self.out_h[n_obs + n_rw:].view(torch.int32).numpy()
+        base_d = self.in_d[:2].view(torch.int32)
+        actions_d = self.in_d[2:].view(P, B)
+        states_d = self.out_d[:n_obs].view(P, B, O + 2)
+        rewards_d = self.out_d[n_obs:n_obs + n_rw].view(P, B)
+        stamp_d = self.out_d[n_obs + n_rw:].view(torch.int32)            # private stamp (launch numbers only grow)
+        self.stream = torch.cuda.Stream(device=dev)
+        self.graph = torch.cuda.CUDAGraph()
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.no_grad(), torch.cuda.graph(self.graph, stream=self.stream):
+            self.in_d.copy_(self.in_h, non_blocking=True)
+            env.step_into(actions_d, states_d, rewards_d, base_d, 1, stamp=stamp_d)
+            self.out_h.copy_(self.out_d, non_blocking=True)
+
+    def step(self, actions):
+        """actions: [P,B] integer CPU tensor (or numpy array) -> (states [P,B,O+2], rewards [P,B]) on the host."""
+        env = self.env
+        if torch.is_tensor(actions):
+            actions = actions.numpy()                      # (CPU tensors only; shares memory)
+        if tuple(actions.shape) != tuple(self.actions_h.shape):
+            raise ValueError('actions must have shape [num_players, num_boards] = %s' % (tuple(self.actions_h.shape),))
+        anybody_alive = env._any_alive()
+        if not anybody_alive:                              # games/race.py:353-356 (19-wide quirk), on the host
+            env.steps += 1
+            P, B, O = env.num_players, env.num_tracks, env.observation_size
+            rewards = (1. - env.finishes.float().cpu()) * env.negative_reward
+            return torch.zeros((P, B, O + 1), dtype=torch.float32), rewards.t()
+        np.copyto(self._actions_np, actions, casting='unsafe')
+        self._base_np[0], self._base_np[1] = env.steps, env._seq
+        self.graph.replay()                                # on the caller's stream: ordered after its reset / restore
+        torch.cuda.current_stream(env.device).synchronize()
+        env.steps += 1
+        env._seq += 1
+        env._alive_known = bool((self._stamp_np == env._seq).any())
+        return self.states_h, self.rewards_h

@@ -136,10 +136,12 @@ int glg_race_init(glg_race_state state, int32_t B, int32_t P, int32_t* alive_sta
  *   alive_stamp [GLG_ALIVE_SLOTS] i32 or NULL: slot (b % GLG_ALIVE_SLOTS) := max(slot, launch_seq) if track b still
  *              has an alive car after this step (host reads it for Race.finished(), race.py:502-504)
  *   launch_seq a number the caller increases with every launch on this environment (> 0)
- *   base       NULL, or a device pointer to {step_no offset, launch_seq offset} (2 x i32) that the kernel adds to
- *              step_no / launch_seq: a launch captured in a CUDA graph is replayed with the running numbers
- *              kept in memory.  With `base`, a step whose number exceeds steps_limit + 1 (the episode timed
- *              out, race.py:502-504) does nothing, so a graph may run past the end of the episode.
+ *   base       NULL, or a device pointer to {step_no offset, launch_seq offset, last step} (3 x i32): the kernel
+ *              adds the first two to step_no / launch_seq - a launch captured in a CUDA graph is replayed with
+ *              the running numbers kept in memory - and does nothing if the resulting step number exceeds
+ *              the third, so a graph may run past the end of an episode (steps_limit + 1 is the last step
+ *              before Race.finished() reports the time-out, race.py:502-504; INT32_MAX = no limit, like
+ *              Race.step itself).
  *   history    optional [>= step_no+1, P, 6] f32 ring written for track `record_id`
  *              (x, y, dx, dy, masked action, alive) at row step_no (race.py:492-494), or NULL
  *   variant    GLG_STEP_PACKED, GLG_STEP_FAST, GLG_STEP_SCAN or GLG_STEP_BRUTE (identical results)  */

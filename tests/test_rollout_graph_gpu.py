@@ -72,3 +72,45 @@ def test_graphed_rollout_matches_the_reference_loop(timeout, k):
     assert eq(env.winners(), env2.winners())
     if timeout > 10:
         assert int(env.finishes.sum()) + int((~env.alive).sum()) > 0
+
+
+def test_host_stepper_matches_step():
+    """HostStepper (one CUDA graph per step, host buffers) against Race.step, through deaths, the time limit and
+    the 19-wide early-out, and across a rewind."""
+    from game_level_gan_b200.games import Race, RaceConfig
+    g = torch.Generator().manual_seed(8)
+    B, T = 200, 70
+    tracks = torch.zeros(B, 128, 2)
+    tracks[:, :, 0] = torch.linspace(-1., 1., 9)[torch.randint(0, 9, (B, 128), generator=g)]
+    acts = torch.randint(0, 9, (T, 2, B), generator=g)
+    acts[:, :, ::3] = 1
+    a = Race(timeout=3., cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
+    b = Race(timeout=3., cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
+    a.reset(tracks)
+    b.reset(tracks)
+    hs = b.host_stepper()
+    snap = b.snapshot()
+    for s in range(5):
+        hs.step(acts[s])
+    b.restore(snap)
+    for s in range(T):
+        sa, ra = a.step(acts[s].cuda())
+        sb, rb = hs.step(acts[s] if s % 2 else acts[s].numpy())
+        assert sb.device.type == 'cpu' and eq(sa, sb) and eq(ra, rb), 'step %d' % s
+        assert a.finished() == b.finished() and a.steps == b.steps
+    assert eq(a.positions, b.positions) and eq(a.scores, b.scores) and eq(a.winners(), b.winners())
+    assert a.finished()
+    # everybody dead: tiny batch of cars driving into the wall
+    c = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
+    d = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
+    tr = tracks[:4]
+    c.reset(tr); d.reset(tr)
+    hd = d.host_stepper()
+    right = torch.full((2, 4), 4, dtype=torch.int64)          # forward-right until the wall
+    for s in range(400):
+        sc, rc = c.step(right.cuda())
+        sd, rd = hd.step(right)
+        assert sc.shape == sd.shape and eq(sc, sd) and eq(rc, rd), 'step %d' % s
+        if sc.size(-1) == 19:
+            break
+    assert sc.size(-1) == 19 and c.finished() and d.finished()
