@@ -226,3 +226,32 @@ def test_reset_from_generator_levels():
         acts[:, ::2] = 1
         (sa, ra), (sc, rc) = a.step(acts.cuda()), c2.step(acts.cuda())
         assert eq(sa, sc) and eq(ra, rc) and eq(a.positions, c2.positions) and eq(a.scores, c2.scores)
+
+
+@pytest.mark.parametrize('P', [1, 3, 4])
+def test_chained_rollout_other_player_counts(P):
+    """Chained rollouts (LL hand-over with keep_all, release/acquire stamps without) for 1, 3 and 4 cars per
+    track - an idle half warp, two warps per track - against per-step calls."""
+    from game_level_gan_b200.games import Race, RaceCar
+    cars = [RaceCar(*c) for c in [(60., 4., 40.), (60., 1., 80.), (80., 2., 60.), (50., 3., 50.)][:P]]
+    g = torch.Generator().manual_seed(40 + P)
+    B, T = 301, 45
+    tracks = torch.zeros(B, 128, 2)
+    tracks[:, :, 0] = torch.linspace(-1., 1., 9)[torch.randint(0, 9, (B, 128), generator=g)]
+    acts = torch.randint(0, 9, (T, P, B), generator=g)
+    acts = torch.where(torch.rand((T, P, B), generator=g) < 0.5, torch.ones_like(acts), acts)
+    a = Race(timeout=40., cars=cars, framerate=1. / 20., log_history=False)
+    a.reset(tracks)
+    per_step = [a.step(acts[s].cuda()) for s in range(T)]
+    for keep_all in (True, False):
+        b = Race(timeout=40., cars=cars, framerate=1. / 20., log_history=False)
+        b.reset(tracks)
+        states, rewards = b.rollout(acts.cuda(), keep_all=keep_all)
+        if keep_all:
+            assert eq(states, torch.stack([s for s, _ in per_step])) and eq(rewards, torch.stack([r for _, r in per_step]))
+        else:
+            assert eq(states, per_step[-1][0]) and eq(rewards, per_step[-1][1])
+        for x, y in ((a.positions, b.positions), (a.directions, b.directions), (a.speeds, b.speeds),
+                     (a.alive, b.alive), (a.finishes, b.finishes), (a.scores, b.scores)):
+            assert eq(x, y)
+        assert a.finished() == b.finished() and eq(a.winners(), b.winners())
