@@ -19,7 +19,7 @@ int launch_status(const char* what);
         }                                        \
     } while (0)
 
-// Optional per-phase cycle accounting of the step kernel (scratch builds with -DGLG_PHASE_CLOCKS only):
+// Optional per-phase cycle accounting of the step kernel (debug builds with -DGLG_PHASE_CLOCKS only):
 // lane 0 of every warp adds the cycles since its previous mark to g_phase[i]; read with glg_debug_phases().
 #ifdef GLG_PHASE_CLOCKS
 static __device__ unsigned long long g_phase[32];   // one copy per translation unit; only glg_race.cu uses it

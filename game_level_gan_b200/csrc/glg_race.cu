@@ -11,8 +11,6 @@
 // kinematics, progress arg-min, wall/finish collision, reward/score, and the ray-cast sensors for
 // its car with the lanes striding over points / walls, and packs the [P,B,O+2] observation.
 // There is no cross-car dependence in the reference step, so no global sync.
-#include <stdlib.h>
-
 #include "glg_common.cuh"
 #include "glg_exact.cuh"
 #include "glg_sensors.cuh"
@@ -375,8 +373,6 @@ static void launch_one(const glg_race_params* pr, const StepArgs& a, cudaStream_
     cfg.gridDim = dim3(a.B);
     cfg.blockDim = dim3(32 * pr->num_players);
     cfg.dynamicSmemBytes = smem_total(a.N, pr->num_players);
-    static const int pad = getenv("GLG_SMEM_PAD") ? atoi(getenv("GLG_SMEM_PAD")) : 0;   // occupancy experiments
-    cfg.dynamicSmemBytes += pad;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see griddepcontrol in the kernel
@@ -406,16 +402,10 @@ static void launch_packed(const glg_race_params* pr, const StepArgs& a, cudaStre
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((a.B + TPB - 1) / TPB);
     cfg.blockDim = dim3(32 * WPT * TPB);
-    // Measured (chained rollouts, config 2): throughput peaks at ~16 resident 64-thread CTAs per SM and falls
-    // off on both sides (14: -3 %, 21: -13 %), so the launch asks for at least 1/16 of the SM's shared memory.
-    // (only the two-tracks-per-CTA shape; one track of 4 cars per CTA is fastest unconstrained: 9.7e8 vs 9.3e8)
-    static const int ctas = getenv("GLG_PACKED_CTAS_PER_SM") ? atoi(getenv("GLG_PACKED_CTAS_PER_SM")) : (TPB == 2 ? 16 : 0);
-    size_t smem = (size_t)TPB * pk_track_bytes(a.N, 2 * WPT);
-    if (ctas > 0) {
-        const size_t share = ((size_t)(228 * 1024) / (size_t)ctas - 1024) & ~(size_t)127;   // 1 KB per CTA is reserved by the system
-        if (smem < share) smem = share;
-    }
-    cfg.dynamicSmemBytes = smem;
+    // Residency: the two-tracks-per-CTA shape (64 registers) holds 16 CTAs per SM, which is where a chained config-2
+    // rollout peaks (a launch has 2048 CTAs: more slots only hold CTAs that wait for their predecessor; measured
+    // with 48 registers: 14 CTAs/SM -3 %, 18 -7 %, 21 -13 %).  One track of 3..8 cars per CTA runs unconstrained.
+    cfg.dynamicSmemBytes = (size_t)TPB * pk_track_bytes(a.N, 2 * WPT);
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

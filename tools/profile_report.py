@@ -1,6 +1,6 @@
 """profiles/<name>.md from an ncu report: headline metrics, warp stall breakdown, hottest source lines.
 
-    python scratch/profile_report.py gpurun_out/prof_X.ncu-rep profiles/X_step_kernel.md "title" [cars]
+    python tools/profile_report.py gpurun_out/prof_X.ncu-rep profiles/X_step_kernel.md "title" [cars]
 """
 import csv, subprocess, sys, io
 rep, out, title = sys.argv[1], sys.argv[2], sys.argv[3]
