@@ -108,12 +108,13 @@ def _c_oracle_for(env, case_cars, framerate, timeout):
     return c_oracle.CRace(out)
 
 
-@pytest.mark.parametrize('P', [2, 4])
+@pytest.mark.parametrize('P', [2, 4, 7])
 def test_free_running_rollout_vs_c_oracle(P):
     """100-step free-running rollout on 512 iid-9 tracks, random + forward-biased actions: CUDA (fast and
     brute) against the C oracle, every step, every output - bit-exact."""
     from game_level_gan_b200.games import Race, RaceCar, _tables
-    cars = [(60., 4., 40.), (60., 1., 80.), (80., 2., 60.), (50., 3., 50.)][:P]
+    cars = [(60., 4., 40.), (60., 1., 80.), (80., 2., 60.), (50., 3., 50.), (70., 2., 30.), (40., 4., 90.),
+            (90., 1., 45.)][:P]
     g = torch.Generator().manual_seed(99)
     B, T = 512, 100
     space = torch.linspace(-1., 1., 9)
@@ -228,12 +229,13 @@ def test_reset_from_generator_levels():
         assert eq(sa, sc) and eq(ra, rc) and eq(a.positions, c2.positions) and eq(a.scores, c2.scores)
 
 
-@pytest.mark.parametrize('P', [1, 3, 4])
+@pytest.mark.parametrize('P', [1, 3, 4, 8])
 def test_chained_rollout_other_player_counts(P):
     """Chained rollouts (LL hand-over with keep_all, release/acquire stamps without) for 1, 3 and 4 cars per
     track - an idle half warp, two warps per track - against per-step calls."""
     from game_level_gan_b200.games import Race, RaceCar
-    cars = [RaceCar(*c) for c in [(60., 4., 40.), (60., 1., 80.), (80., 2., 60.), (50., 3., 50.)][:P]]
+    cars = [RaceCar(*c) for c in [(60., 4., 40.), (60., 1., 80.), (80., 2., 60.), (50., 3., 50.), (70., 2., 30.),
+                                  (40., 4., 90.), (90., 1., 45.), (55., 2., 70.)][:P]]
     g = torch.Generator().manual_seed(40 + P)
     B, T = 301, 45
     tracks = torch.zeros(B, 128, 2)
@@ -255,3 +257,42 @@ def test_chained_rollout_other_player_counts(P):
                      (a.alive, b.alive), (a.finishes, b.finishes), (a.scores, b.scores)):
             assert eq(x, y)
         assert a.finished() == b.finished() and eq(a.winners(), b.winners())
+
+
+@pytest.mark.parametrize('O,max_distance', [(8, 10.), (9, 6.), (32, 10.), (18, 3.)])
+def test_other_ray_counts_and_ranges(O, max_distance):
+    """observation_size / max_distance other than the defaults (games/race.py:26): even ray counts run the
+    single-pass pruning kernel, odd ones the literal loop; both against the torch oracle and the C oracle."""
+    from game_level_gan_b200.games import Race, RaceCar, _tables
+    from oracle import c_oracle
+    from oracle import race_oracle as ro
+    cars = [(60., 4., 40.), (60., 1., 80.)]
+    g = torch.Generator().manual_seed(1000 + O)
+    B, T = 96, 40
+    tracks = torch.zeros(B, 128, 2)
+    tracks[:, :, 0] = torch.linspace(-1., 1., 9)[torch.randint(0, 9, (B, 128), generator=g)]
+    acts = torch.randint(0, 9, (T, 2, B), generator=g)
+    acts = torch.where(torch.rand((T, 2, B), generator=g) < 0.5, torch.ones_like(acts), acts)
+    pr = _tables.race_params([ro.Car(*c) for c in cars], 1. / 20., 40., O, max_distance)
+    cpr = c_oracle.RaceParams()
+    ctypes.memmove(ctypes.byref(cpr), ctypes.byref(pr), ctypes.sizeof(cpr))
+    orc = c_oracle.CRace(cpr)
+    st, ct, _ = _tables.heading_tables(128)
+    so, _ = orc.reset(tracks.numpy(), st.numpy(), ct.numpy())
+    tor = ro.RaceOracle(timeout=40., cars=[ro.Car(*c) for c in cars], observation_size=O, max_distance=max_distance,
+                        framerate=1. / 20.)
+    s_t, _ = tor.reset(tracks)
+    envs = {v: Race(timeout=40., cars=[RaceCar(*c) for c in cars], observation_size=O, max_distance=max_distance,
+                    framerate=1. / 20., log_history=False, variant=v) for v in ('fast', 'brute')}
+    for v, env in envs.items():
+        s0, _ = env.reset(tracks)
+        assert s0.shape == (2, B, O + 2) and eq(s0, so) and eq(s0, s_t), v
+    for s in range(T):
+        so, ro_ = orc.step(acts[s].numpy())
+        s_t, r_t = tor.step(acts[s]) if s < 12 else (None, None)          # the torch oracle is slow: first steps only
+        for v, env in envs.items():
+            sg, rg = env.step(acts[s].cuda())
+            assert eq(sg, so) and eq(rg, ro_), (v, s)
+            if s_t is not None:
+                assert eq(sg, s_t) and eq(rg, r_t), (v, s)
+            assert eq(env.positions, orc.pos) and eq(env.scores, orc.scores)
