@@ -28,7 +28,8 @@ struct PackedCar {                             // per-car shared scratch
     float4 ray[PK_RAYS];                       // dx, dy, far x, far y
     int tmin[PK_RAYS + 2];                     // running min of t as ordered int bits
     unsigned nan_mask;
-    unsigned pad[3];
+    int qn;                                    // rays queued for the second evaluation round
+    unsigned pad[2];
 };
 
 // shared memory per track: [record 3N float2][mbarrier 16 B][cars x PackedCar][cars x cq u16[LL]][cars x wlist u16[2N]]
@@ -316,7 +317,7 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
             car->tmin[PK_G + gl] = 0x7f800000;
         }
     }
-    if (gl == 0) car->nan_mask = 0;
+    if (gl == 0) { car->nan_mask = 0; car->qn = 0; }
 
     const float Lmax = ext.y;
     const float Rc = fmaf(RC_FACTOR, Lmax, 1e-3f);
@@ -509,57 +510,49 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
     }
 
     GLG_MARK(8);
-    // ---- stage 2: candidate rays of the flagged walls -> queue ----
-    int total = 0;
-    bool overflow = false;
+    // ---- stage 2: candidate rays of the flagged walls; the first ray of a wall is evaluated on the spot ----
+    // (race.py:287-308; most flagged walls have exactly one candidate ray: the lane already holds the wall, so the
+    //  exact test runs right here and only the 2nd, 3rd, ... rays of a wall go through the queue)
+    const bool sense = alive && scan_on;                       // `alive` is post-update here: dead cars report zeros
     {
         const unsigned all_rays = (1u << O) - 1u;
         const float sect = (float)O * (0.5f / PI_F);
         const float m_eta = ETA_ANGLE * sect, m_eps = EPS_PERP * sect, fhalf = 0.5f * (float)O;
-        const int nwmax = (int)__reduce_max_sync(FULL, (unsigned)nw);
-        for (int base = 0; base < nwmax; base += PK_G) {
-            const int e = base + gl;
-            unsigned mask = 0;
-            int w = 0;
-            if (e < nw) {
-                w = wlist[e];
+        const int nws = sense ? nw : 0;
+        const int nwmax = (int)__reduce_max_sync(FULL, (unsigned)nws);
+        for (int base = gl; base < nwmax; base += PK_G) {
+            if (base < nws) {
+                const int w = wlist[base];
                 const float2 p0 = tv.line[w], p1 = tv.line[w + 1];
-                mask = wall_ray_mask(p0.x - np.x, p0.y - np.y, p1.x - np.x, p1.y - np.y, nd, O, sect, fhalf, m_eps, m_eta, all_rays);
-            }
-            const int cnt = __popc(mask);
-            int incl = cnt;
-#pragma unroll
-            for (int off = 1; off < PK_G; off <<= 1) {
-                const int t = __shfl_up_sync(FULL, incl, off, PK_G);
-                if (gl >= off) incl += t;
-            }
-            const int tot = __shfl_sync(FULL, incl, PK_G - 1, PK_G);
-            if (total + tot > PK_QCAP) overflow = true;
-            if (!overflow) {
-                int posn = total + incl - cnt;
-                const int wcode = w << 5;
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {                              // straight-line for the usual <= 2 rays per wall
-                    if (mask) {
-                        const int i = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        cq[posn++] = (unsigned short)(wcode | i);
-                    }
-                }
-                while (mask) {
+                unsigned mask = wall_ray_mask(p0.x - np.x, p0.y - np.y, p1.x - np.x, p1.y - np.y, nd, O, sect, fhalf, m_eps, m_eta, all_rays);
+                if (mask) {
                     const int i = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    cq[posn++] = (unsigned short)(wcode | i);
+                    const bool rev = w < N;                            // wall_by_line_index
+                    const P2 pp = rev ? P2{p1.x, p1.y} : P2{p0.x, p0.y}, qq = rev ? P2{p0.x, p0.y} : P2{p1.x, p1.y};
+                    const float4 r = car->ray[i];
+                    const float t = ray_wall_t_fast(pp, qq, np, P2{r.x, r.y}, P2{r.z, r.w});
+                    if (t != t) atomicOr(&car->nan_mask, 1u << i);
+                    else atomicMin(&car->tmin[i], __float_as_int(t));
+                    if (mask) {                                        // further rays of this wall: second round
+                        int posn = atomicAdd(&car->qn, __popc(mask));
+                        const int wcode = w << 5;
+                        while (mask && posn < PK_QCAP) {
+                            cq[posn++] = (unsigned short)(wcode | (__ffs(mask) - 1));
+                            mask &= mask - 1;
+                        }
+                    }
                 }
-                total += tot;
             }
         }
     }
+    __syncwarp();
+    const int total = car->qn;                                         // > PK_QCAP: some rays were dropped -> brute force
+    const bool overflow = total > PK_QCAP;
 
     GLG_MARK(9);
-    // ---- exact evaluation of the candidates (race.py:287-308), brute force where the pruning did not apply ----
-    __syncwarp();
-    if (alive && safe && !overflow) {
+    // ---- second round: the queued rays ----
+    if (sense && !overflow) {
         for (int e = gl; e < total; e += PK_G) {
             const int code = cq[e];
             const int w = code >> 5, i = code & 31;
