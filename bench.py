@@ -252,6 +252,9 @@ def run_b200(args, rank, world):
             i += 1
 
     run_steps(max(args.warmup, 3))
+    if world > 1:       # warm-up of the collective too (communicator set-up is not part of a step)
+        from game_level_gan_b200 import dist as gdist
+        gdist.all_gather_winners(reps[0].env.winners())
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
