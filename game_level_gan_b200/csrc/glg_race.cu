@@ -6,7 +6,10 @@
 //   glg_race_winners  games/race.py:506-529   Race.winners
 //   glg_winner_stats  train-gan.py:103-104    one_hot(winners+1).view(trials,-1,P+1).mean(0)
 //
-// Mapping: one CTA per track, one warp per car.  The CTA stages the track record
+// Production kernel: race_step_packed_kernel (glg_race_packed.cuh, two cars per warp).  This file holds the
+// launch logic and race_step_kernel<VARIANT>, the same step with one CTA per track and one warp per car:
+// FAST (the packed kernel's algorithm; long or odd-length tracks), SCAN (single-pass pruning; other even ray
+// counts) and BRUTE (the literal loops; odd ray counts, verification).  The CTA stages the track record
 // {line, centre} (3*N float2, 3120 B at L=128) in shared memory with one bulk async copy (TMA); each warp then runs
 // kinematics, progress arg-min, wall/finish collision, reward/score, and the ray-cast sensors for
 // its car with the lanes striding over points / walls, and packs the [P,B,O+2] observation.

@@ -4,10 +4,12 @@
 // what changes is the mapping.  A warp owns a track's cars 2w and 2w+1 ("groups" of 16 lanes), so that
 //   * the per-car scalar work (state loads, kinematics, reward, write-back, address arithmetic) is issued
 //     once per two cars instead of once per car,
-//   * the list phases (flagged walls -> candidate rays -> exact evaluation) run 16 entries per car per
-//     pass: ~45 flagged walls and ~35 candidates per car fill 3 passes of a half warp instead of 2 + 2.2
-//     passes of a full warp each,
+//   * the list phase (flagged walls -> candidate rays -> exact evaluation) runs 16 walls per car per pass:
+//     ~45 flagged walls per car fill 3 passes of a half warp, each lane evaluating the first candidate ray
+//     of its wall on the spot (only further rays of a wall are queued for a short second round),
 //   * the vertex pass (stage 1) costs the same (17 half-warp passes for two cars = 8.5 per car).
+// Rollouts chain consecutive launches car by car (glg_race_rollout); with keep_all the car state is handed
+// from launch to launch in self-validating 64-bit words ("LL") instead of through the state arrays.
 // Included by glg_race.cu after StepArgs.
 #pragma once
 #include "glg_common.cuh"
