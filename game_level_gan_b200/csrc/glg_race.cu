@@ -319,6 +319,8 @@ race_step_kernel(const __grid_constant__ glg_race_params pr, const StepArgs a)
     }
     GLG_MARK(12);
     GLG_TRACE(2);
+    // (see race_step_packed_kernel: makes chained launches complete in order)
+    if (a.chained) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 __global__ void race_winners_kernel(const int32_t* __restrict__ scores, const uint8_t* __restrict__ finishes,

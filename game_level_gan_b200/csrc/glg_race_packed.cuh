@@ -601,6 +601,10 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
             asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(a.chain + k), "r"(seq) : "memory");
         }
     }
+    // A chained launch never waited for the previous grid as a whole.  Waiting for it here, after the work, costs
+    // nothing in steady state (the previous step's CTAs are done by now) and makes launches COMPLETE in order, so
+    // that whatever follows the rollout in the stream finds every step's outputs and scores in memory.
+    if (a.chained) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 }  // namespace glg
