@@ -12,9 +12,12 @@ CYCLE steps a replica's car state is rewound to its mid-race snapshot (6 small d
 timed region) and the same tape is replayed, so ~100 % of the cars are alive throughout - dead cars skip
 the ray cast and would inflate the number.  The alive fraction at both ends of the cycle is reported.
 
-`value`  : device-resident throughput, CUDA events around the K launches (max over ranks).
-`e2e`    : the same metric through the public API (`Race.step`) with HOST buffers: pinned actions
-           copied in and observations + rewards copied out every step, inside the timed region.
+`value`  : device-resident throughput, CUDA events around the K launches (max over ranks); the launches of a
+           cycle are one `Race.rollout` (glg_race_rollout: one kernel per step, consecutive steps chained car by
+           car), and every step writes its observations and rewards (keep_all).
+`e2e`    : the same metric through the public API for host-resident callers (`Race.host_stepper().step`):
+           host actions in, host observations + rewards out EVERY step (H2D, step kernel, D2H as one CUDA graph,
+           one synchronisation per step), inside the timed region.
 `roofline`: algorithmic bytes of one launch (3120 B per track + 145 B per car) over the
            average launch duration, against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
 `cpu_baseline`: the reference's algorithm on the host cores - the torch-op restatement (same ATen
