@@ -164,6 +164,17 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
         record_copy_async(pts, reinterpret_cast<const float2*>(a.geom) + (size_t)b * 3 * N, rec_bytes, bar);
     asm volatile("griddepcontrol.launch_dependents;");
     const int k = b * P + p;
+    // Inputs of a chained launch (t >= 1 of a rollout) are older than the rollout itself: fetch them before waiting
+    // for the previous step of the car, so that their latency is off the car's critical path.
+    const bool inputs_early = a.chained != 0;
+    bool ok = false;
+    int act = 0;
+    float2 ext = make_float2(INF, INF);
+    if (inputs_early && car_on) {
+        ok = a.valid[b] != 0;
+        act = (int)a.actions[(size_t)p * B + b];
+        ext = __ldg(reinterpret_cast<const float2*>(a.extent) + b);
+    }
     // "LL" chaining (rollouts that keep every step's outputs): the previous step of this car hands its state
     // over in six 64-bit words {launch number : value} - single-copy atomic, self-validating, so neither side
     // needs a fence and the consumer needs no second round trip for the state itself.
@@ -201,11 +212,9 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
 
     GLG_MARK(0);
     // ---- car state and kinematics (uniform within a group) ----
-    bool alive = false, fin = false, ok = false;
-    int act = 0;
+    bool alive = false, fin = false;
     float2 dir = make_float2(0.f, 1.f), pos = make_float2(0.f, 0.f);
     float spd = 0.f;
-    float2 ext = make_float2(INF, INF);
     if (a.ll_read) {                     // words: pos.x, pos.y, dir.x, dir.y, speed, flags (alive | finished << 1)
         pos.x = __uint_as_float(__shfl_sync(FULL, llw, 0, PK_G));
         pos.y = __uint_as_float(__shfl_sync(FULL, llw, 1, PK_G));
@@ -226,9 +235,11 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
             pos = __ldcg(reinterpret_cast<const float2*>(a.st.positions) + k);
             spd = __ldcg(&a.st.speeds[k]);
         }
-        ok = a.valid[b] != 0;
-        act = (int)a.actions[(size_t)p * B + b];
-        ext = __ldg(reinterpret_cast<const float2*>(a.extent) + b);
+        if (!inputs_early) {
+            ok = a.valid[b] != 0;
+            act = (int)a.actions[(size_t)p * B + b];
+            ext = __ldg(reinterpret_cast<const float2*>(a.extent) + b);
+        }
     }
     const int pc = min(p, GLG_MAX_PLAYERS - 1);
     act = min(max(act, 0), 8);
@@ -244,7 +255,8 @@ race_step_packed_kernel(const __grid_constant__ glg_race_params pr, const StepAr
     const P2 np{xadd(pos.x, xmul(nd.x, nv)), xadd(pos.y, xmul(nd.y, nv))};   // race.py:372
 
     GLG_MARK(1);
-    __syncthreads();                     // mbarrier init visible to the other warps of the track
+    if (TPB == 2) __syncwarp();          // one warp per track: the lane that initialised the mbarrier is in this warp
+    else __syncthreads();                // mbarrier init visible to the other warps of the track
     if (track_on) record_copy_wait(bar);
     const TrackView tv{pts, pts + 2 * N, N};
 
