@@ -230,6 +230,9 @@ def run_b200(args, rank, world):
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
     if world > 1:
+        # stdout carries ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints it to stdout) out of it
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=device)
     import __graft_entry__ as entry
     if rank == 0:
