@@ -230,10 +230,19 @@ def run_b200(args, rank, world):
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
     if world > 1:
-        # stdout carries ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints it to stdout) out of it
-        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'
-        dist.init_process_group('nccl', device_id=device)
+        # stdout carries ONE JSON line: NCCL prints its version banner to stdout when the communicator is created,
+        # so file descriptor 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     import __graft_entry__ as entry
     if rank == 0:
         entry.build()
