@@ -75,24 +75,47 @@ __global__ void pacman_apply_kernel(int32_t* __restrict__ grid, int32_t* __restr
     }
 }
 
-// one thread per grid cell: reads 4+P ints once, writes P rows of 4+2P floats
+// one thread per grid cell: reads 4+P ints once, writes P rows of 4+2P floats.
+// PC = compile-time number of players (0 = generic): with it the per-cell arrays live in registers and the row of
+// an even-sized observation goes out as float4 stores.
+template <int PC>
 __global__ void pacman_observe_kernel(const int32_t* __restrict__ grid, float* __restrict__ obs,
-                                      size_t cells, int P)
+                                      size_t cells, int P_rt)
 {
     const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= cells) return;
-    const int C = 4 + P, D = 4 + 2 * P;
-    float v[4 + GLG_MAX_PLAYERS];
-    for (int c = 0; c < C; ++c) v[c] = (float)grid[cell * C + c];
-    for (int p = 0; p < P; ++p) {
-        float* o = obs + ((size_t)p * cells + cell) * D;
-        if ((D & 3) == 0) {
-            float tmp[4 + 2 * GLG_MAX_PLAYERS];
-            for (int c = 0; c < D; ++c) tmp[c] = c < C ? v[c] : (c == C + p ? 1.f : 0.f);
-            for (int c = 0; c < D; c += 4)
-                *reinterpret_cast<float4*>(o + c) = make_float4(tmp[c], tmp[c + 1], tmp[c + 2], tmp[c + 3]);
+    if (PC > 0) {
+        constexpr int C = 4 + PC, D = 4 + 2 * PC;
+        float v[C];
+        if ((C & 1) == 0) {                                                // 8-byte aligned rows
+            const int2* g = reinterpret_cast<const int2*>(grid + cell * C);
+#pragma unroll
+            for (int c = 0; c < C / 2; ++c) { const int2 t = __ldg(g + c); v[2 * c] = (float)t.x; v[2 * c + 1] = (float)t.y; }
         } else {
-            for (int c = 0; c < D; ++c) o[c] = c < C ? v[c] : (c == C + p ? 1.f : 0.f);
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[c] = (float)__ldg(grid + cell * C + c);
+        }
+#pragma unroll
+        for (int p = 0; p < PC; ++p) {
+            float* o = obs + ((size_t)p * cells + cell) * D;
+            float row[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) row[c] = c < C ? v[c] : (c == C + p ? 1.f : 0.f);
+            if ((D & 3) == 0) {
+#pragma unroll
+                for (int c = 0; c < D; c += 4)
+                    __stcs(reinterpret_cast<float4*>(o + c), make_float4(row[c], row[c + 1], row[c + 2], row[c + 3]));
+            } else {
+#pragma unroll
+                for (int c = 0; c < D; c += 2)
+                    __stcs(reinterpret_cast<float2*>(o + c), make_float2(row[c], row[c + 1]));
+            }
+        }
+    } else {
+        const int P = P_rt, C = 4 + P, D = 4 + 2 * P;
+        for (int p = 0; p < P; ++p) {
+            float* o = obs + ((size_t)p * cells + cell) * D;
+            for (int c = 0; c < D; ++c) o[c] = c < C ? (float)grid[cell * C + c] : (c == C + p ? 1.f : 0.f);
         }
     }
 }
@@ -124,6 +147,14 @@ extern "C" int glg_pacman_observe(const int32_t* grid, float* obs, int32_t B, in
     const size_t cells = (size_t)B * H * W;
     if (cells == 0) return GLG_OK;
     GLG_REQUIRE(grid && obs, "glg_pacman_observe: null pointer");
-    pacman_observe_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, (cudaStream_t)stream>>>(grid, obs, cells, P);
+    const unsigned blocks = (unsigned)((cells + 255) / 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (P) {
+        case 1: pacman_observe_kernel<1><<<blocks, 256, 0, s>>>(grid, obs, cells, P); break;
+        case 2: pacman_observe_kernel<2><<<blocks, 256, 0, s>>>(grid, obs, cells, P); break;
+        case 3: pacman_observe_kernel<3><<<blocks, 256, 0, s>>>(grid, obs, cells, P); break;
+        case 4: pacman_observe_kernel<4><<<blocks, 256, 0, s>>>(grid, obs, cells, P); break;
+        default: pacman_observe_kernel<0><<<blocks, 256, 0, s>>>(grid, obs, cells, P); break;
+    }
     return launch_status("glg_pacman_observe");
 }

@@ -24,3 +24,17 @@ obs_bytes = P * B * H * W * (4 + 2 * P) * 4
 grid_bytes = 2 * B * H * W * (4 + P) * 4
 print('pacman B=%d %dx%d P=%d: %.1f us per step, %.3e board-steps/s, obs write %.0f MB + grid r/w %.0f MB per step -> %.0f GB/s (%.2f of 6549.8)' % (
     B, H, W, P, 1e3 * ms, B / (ms * 1e-3), obs_bytes / 1e6, grid_bytes / 1e6, (obs_bytes + grid_bytes) / (ms * 1e-3) / 1e9, (obs_bytes + grid_bytes) / (ms * 1e-3) / 6549.8e9))
+
+# the two halves separately
+from game_level_gan_b200 import _lib
+from game_level_gan_b200._lib import ptr
+lib = _lib.lib(); stream = _lib.stream_ptr(dev)
+obs = torch.empty((P, B, H, W, 4 + 2 * P), dtype=torch.float32, device=dev)
+rewards = torch.empty((P, B), dtype=torch.float64, device=dev)
+for name, fn in (('observe kernel', lambda t: lib.glg_pacman_observe(ptr(env._grid), ptr(obs), B, H, W, P, stream)),
+                 ('step kernels', lambda t: lib.glg_pacman_step(ptr(env._grid), ptr(env._players), ptr(acts[t]), ptr(rewards), ptr(env._scratch), B, H, W, P, stream))):
+    for t in range(5): fn(t)
+    torch.cuda.synchronize(); e0.record()
+    for t in range(T): fn(t)
+    e1.record(); torch.cuda.synchronize()
+    print('%s: %.1f us' % (name, 1e3 * e0.elapsed_time(e1) / T))
