@@ -1,0 +1,14 @@
+"""Reset cost (geometry build, validity, extents, init, first step) at config 2 and at a config-4 shard."""
+import sys, os, time, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from game_level_gan_b200.games import Race, RaceConfig
+dev = torch.device('cuda', 0); torch.cuda.set_device(0)
+for B in (4096, 131072):
+    tracks = bench.synthetic_tracks(B, 3).to(dev)
+    env = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False, device=dev)
+    for r in range(3):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        env.reset(tracks)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    print('B=%d: reset %.2f ms (%.1f ns per track) valid fraction %.3f' % (B, 1e3 * dt, 1e9 * dt / B, float(env._valid_tracks.float().mean())))
