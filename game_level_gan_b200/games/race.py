@@ -75,6 +75,7 @@ class Race(MultiEnvironment):
         self.positions = self.directions = self.speeds = None
         self._alive = self._finishes = self.scores = None
         self._valid_tracks = None
+        self._epoch = 0                 # number of resets (captured CUDA graphs are bound to one episode's buffers)
 
     # ---- device / constants --------------------------------------------------------------------
     @property
@@ -165,6 +166,7 @@ class Race(MultiEnvironment):
             N, P = L + 2, self.num_players
             self.steps = 0
             self.num_tracks = B
+            self._epoch += 1
             self._lazy = {}
             self._geom = torch.empty((B, 3, N, 2), dtype=torch.float32, device=dev)
             if geometry is not None:

@@ -25,6 +25,7 @@ class GraphedRollout(object):
         if env.num_tracks is None or env.num_tracks == 0:
             raise GlgError('GraphedRollout needs a reset environment with at least one track')
         self.env, self.act, self.k, self.on_reset = env, act, int(steps_per_replay), on_reset
+        self.epoch = env._epoch
         dev = env.device
         B, P, O = env.num_tracks, env.num_players, env.observation_size
         self.states = torch.zeros((P, B, O + 2), dtype=torch.float32, device=dev)
@@ -62,6 +63,9 @@ class GraphedRollout(object):
         """Play the episode from the observation `states` (of `reset` or the last `step`) to its end.
         Returns (last states, last rewards)."""
         env = self.env
+        if env._epoch != self.epoch:
+            raise GlgError('the environment was reset after this GraphedRollout was created: the graph is bound to '
+                           'the previous episode\'s buffers - create a new one')
         if self.graph is None:
             self.capture()
         self.states.copy_(states)
@@ -101,6 +105,7 @@ class HostStepper(object):
         if env.num_tracks is None or env.num_tracks == 0:
             raise GlgError('HostStepper needs a reset environment with at least one track')
         self.env = env
+        self.epoch = env._epoch
         dev = env.device
         B, P, O = env.num_tracks, env.num_players, env.observation_size
         # one input block {step counters (16 B) | actions} and one output block {observations | rewards | alive stamp}
@@ -133,6 +138,9 @@ class HostStepper(object):
     def step(self, actions):
         """actions: [P,B] integer CPU tensor (or numpy array) -> (states [P,B,O+2], rewards [P,B]) on the host."""
         env = self.env
+        if env._epoch != self.epoch:
+            raise GlgError('the environment was reset after this HostStepper was created: the graph is bound to the '
+                           'previous episode\'s buffers - call host_stepper() again')
         if torch.is_tensor(actions):
             actions = actions.numpy()                      # (CPU tensors only; shares memory)
         if tuple(actions.shape) != tuple(self.actions_h.shape):

@@ -114,3 +114,8 @@ def test_host_stepper_matches_step():
         if sc.size(-1) == 19:
             break
     assert sc.size(-1) == 19 and c.finished() and d.finished()
+    # a stepper is bound to its episode
+    from game_level_gan_b200._lib import GlgError
+    d.reset(tr)
+    with pytest.raises(GlgError):
+        hd.step(right)
