@@ -296,3 +296,79 @@ def test_other_ray_counts_and_ranges(O, max_distance):
             if s_t is not None:
                 assert eq(sg, s_t) and eq(rg, r_t), (v, s)
             assert eq(env.positions, orc.pos) and eq(env.scores, orc.scores)
+
+
+@pytest.mark.parametrize('P', [2, 3])
+def test_unpruned_fallback_paths(P):
+    """Cars for which a precondition of the pruning fails (heading norm far from 1, car far from the origin) take
+    the brute-force path INSIDE the production kernels: force that state and compare packed / warp / scan with
+    the literal kernel, step by step and through a chained rollout."""
+    from game_level_gan_b200.games import Race, RaceCar
+    cars = [RaceCar(*c) for c in [(60., 4., 40.), (60., 1., 80.), (80., 2., 60.)][:P]]
+    g = torch.Generator().manual_seed(77 + P)
+    B, T = 64, 24
+    tracks = torch.zeros(B, 128, 2)
+    tracks[:, :, 0] = torch.linspace(-1., 1., 9)[torch.randint(0, 9, (B, 128), generator=g)]
+    acts = torch.randint(0, 9, (T, P, B), generator=g)
+    acts = torch.where(torch.rand((T, P, B), generator=g) < 0.5, torch.ones_like(acts), acts)
+    envs = {v: Race(timeout=40., cars=cars, framerate=1. / 20., log_history=False, variant=v)
+            for v in ('brute', 'fast', 'warp', 'scan')}
+    for env in envs.values():
+        env.reset(tracks)
+        for s in range(4):
+            env.step(acts[s].cuda())
+        # headings with |d|^2 = 2.56 (outside (0.5, 2)) on every 3rd track, cars moved 300 units away on every 5th
+        env.directions[::3] *= 1.6
+        env.positions[::5] += 300.
+        env.directions[1::7] *= 0.5
+    ref = envs['brute']
+    for s in range(4, 14):
+        so, ro_ = ref.step(acts[s].cuda())
+        for v in ('fast', 'warp', 'scan'):
+            sg, rg = envs[v].step(acts[s].cuda())
+            assert eq(sg, so) and eq(rg, ro_), (v, s)
+            assert eq(envs[v].positions, ref.positions) and eq(envs[v].alive, ref.alive) and eq(envs[v].scores, ref.scores)
+    so, ro_ = ref.rollout(acts[14:].cuda(), keep_all=True)
+    for v in ('fast', 'warp', 'scan'):
+        sg, rg = envs[v].rollout(acts[14:].cuda(), keep_all=True)
+        assert eq(sg, so) and eq(rg, ro_), v
+        assert eq(envs[v].positions, ref.positions) and eq(envs[v].winners(), ref.winners())
+    assert float(so[..., :18].abs().sum()) > 0.
+
+
+def test_degenerate_car_on_the_wall_line():
+    """Straight tracks with cars placed exactly ON a boundary line (and on the start line): every collinear wall
+    becomes a candidate for all rays (queue overflow -> in-kernel brute force), the forward / backward rays are
+    parallel to the walls they touch (0/0 -> NaN in the reference formula, games/race.py:303-306).  All pruned
+    kernels must reproduce the literal kernel bit for bit, NaNs included, and the C oracle must agree."""
+    from game_level_gan_b200.games import Race, RaceConfig, _tables
+    B = 12
+    tracks = torch.zeros(B, 128, 2)
+    tracks[6:, 40:60, 0] = 0.5                                     # half of them with a bend further on
+    noop = torch.zeros((2, B), dtype=torch.int64)
+    fwd = torch.ones((2, B), dtype=torch.int64)
+    envs = {v: Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False, variant=v)
+            for v in ('brute', 'fast', 'warp', 'scan')}
+    orc = _c_oracle_for(None, [(60., 4., 40.), (60., 1., 80.)], 1. / 20., 40.)
+    st, ct, _ = _tables.heading_tables(128)
+    orc.reset(tracks.numpy(), st.numpy(), ct.numpy())
+    for env in envs.values():
+        env.reset(tracks)
+        env.positions[:, 0, 0] = 0.5                               # car 0 on the right wall's line x = +0.5
+        env.positions[:, 1, 0] = -0.5                              # car 1 on the left wall's line
+        env.positions[::2, :, 1] = 0.                              # every other track: also on the start line
+    orc.pos[:, 0, 0] = 0.5
+    orc.pos[:, 1, 0] = -0.5
+    orc.pos[::2, :, 1] = 0.
+    ref = envs['brute']
+    saw_nan = False
+    for s, a in enumerate([noop, noop, fwd, fwd, noop, fwd]):
+        so, ro_ = ref.step(a.cuda())
+        co, cr = orc.step(a.numpy())
+        assert eq(so, co) and eq(ro_, cr), ('oracle', s)
+        saw_nan = saw_nan or bool(torch.isnan(so).any())
+        for v in ('fast', 'warp', 'scan'):
+            sg, rg = envs[v].step(a.cuda())
+            assert eq(sg, so) and eq(rg, ro_), (v, s)
+            assert eq(envs[v].alive, ref.alive) and eq(envs[v].positions, ref.positions)
+    assert saw_nan or float(so[..., :18].min()) == 0.              # the configuration really is degenerate
