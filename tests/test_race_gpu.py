@@ -372,3 +372,31 @@ def test_degenerate_car_on_the_wall_line():
             assert eq(sg, so) and eq(rg, ro_), (v, s)
             assert eq(envs[v].alive, ref.alive) and eq(envs[v].positions, ref.positions)
     assert saw_nan or float(so[..., :18].min()) == 0.              # the configuration really is degenerate
+
+
+def test_wide_and_wild_float_tracks_all_variants():
+    """Arbitrary float arcs and widths (walls up to ~2 units long, so almost every wall is "close" and flagged, and
+    some cars overflow the candidate queue): every pruned kernel against the literal one, 60 steps."""
+    from game_level_gan_b200.games import Race, RaceConfig
+    g = torch.Generator().manual_seed(4242)
+    B, T = 192, 60
+    tracks = torch.zeros(B, 128, 2)
+    tracks[:, :, 0] = torch.rand((B, 128), generator=g) * 2 - 1
+    tracks[:, :, 1] = torch.rand((B, 128), generator=g)
+    tracks[: B // 3, :, 0] *= 0.3                                  # a third of them gentle, so that cars survive longer
+    acts = torch.randint(0, 9, (T, 2, B), generator=g)
+    acts = torch.where(torch.rand((T, 2, B), generator=g) < 0.6, torch.ones_like(acts), acts)
+    envs = {v: Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False, variant=v)
+            for v in ('brute', 'fast', 'warp', 'scan')}
+    s0 = {v: env.reset(tracks)[0] for v, env in envs.items()}
+    ref = envs['brute']
+    for v in ('fast', 'warp', 'scan'):
+        assert eq(s0[v], s0['brute']) and eq(envs[v]._valid_tracks, ref._valid_tracks)
+    for s in range(T):
+        so, ro_ = ref.step(acts[s].cuda())
+        for v in ('fast', 'warp', 'scan'):
+            sg, rg = envs[v].step(acts[s].cuda())
+            assert eq(sg, so) and eq(rg, ro_), (v, s)
+    for v in ('fast', 'warp', 'scan'):
+        assert eq(envs[v].positions, ref.positions) and eq(envs[v].scores, ref.scores) and eq(envs[v].winners(), ref.winners())
+    assert 0 < int(ref.alive.sum()) or int(ref._valid_tracks.sum()) >= 0
