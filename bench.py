@@ -256,7 +256,7 @@ def run_b200(args, rank, world):
 
     REPLICAS = args.replicas
     reps = [Replica(i, rank, device, args.variant) for i in range(REPLICAS)]
-    alive_start = float(torch.stack([r.snap['tensors'][3].float().mean() for r in reps]).mean())
+    alive_start = float(torch.stack([r.env.alive.float().mean() for r in reps]).mean())     # envs sit at their snapshots
 
     def run_steps(k):
         done, i = 0, 0

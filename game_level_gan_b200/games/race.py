@@ -185,12 +185,17 @@ class Race(MultiEnvironment):
                   'glg_track_validate')
             self._extent = torch.empty((B, 2), dtype=torch.float32, device=dev)
             check(lib.glg_track_extent(ptr(self._geom), B, N, ptr(self._extent), stream), 'glg_track_extent')
-            self.positions = torch.empty((B, P, 2), dtype=torch.float32, device=dev)
-            self.directions = torch.empty((B, P, 2), dtype=torch.float32, device=dev)
-            self.speeds = torch.empty((B, P), dtype=torch.float32, device=dev)
-            self._alive = torch.empty((B, P), dtype=torch.uint8, device=dev)
-            self._finishes = torch.empty((B, P), dtype=torch.uint8, device=dev)
-            self.scores = torch.empty((B, P), dtype=torch.int32, device=dev)
+            # the six state arrays are views of ONE allocation (snapshot / restore are one copy each)
+            K = B * P
+            k4 = (K + 3) // 4 * 4
+            self._state_buf = torch.empty((6 * k4 * 4 + 2 * k4,), dtype=torch.uint8, device=dev)
+            f32 = self._state_buf[:6 * k4 * 4].view(torch.float32)
+            self.positions = f32[0:2 * K].view(B, P, 2)
+            self.directions = f32[2 * k4:2 * k4 + 2 * K].view(B, P, 2)
+            self.speeds = f32[4 * k4:4 * k4 + K].view(B, P)
+            self.scores = f32[5 * k4:5 * k4 + K].view(torch.int32).view(B, P)
+            self._alive = self._state_buf[6 * k4 * 4:6 * k4 * 4 + K].view(B, P)
+            self._finishes = self._state_buf[6 * k4 * 4 + k4:6 * k4 * 4 + k4 + K].view(B, P)
             self._stamp = torch.empty((_lib.ALIVE_SLOTS,), dtype=torch.int32, device=dev)
             self._stamp_host = torch.zeros((_lib.ALIVE_SLOTS,), dtype=torch.int32).pin_memory()
             self._chain = torch.zeros((max(int(lib.glg_race_chain_bytes(B, P)) // 4, 4),), dtype=torch.int32,
@@ -291,15 +296,12 @@ class Race(MultiEnvironment):
     def snapshot(self):
         """Copy of the mutable episode state (the reference has no env checkpoint; used to rewind
         rollouts, e.g. by bench.py).  Geometry and validity are not part of it."""
-        live = (self.positions, self.directions, self.speeds, self._alive, self._finishes, self.scores)
-        return {'tensors': tuple(x.clone() for x in live), 'steps': self.steps,   # _seq is never rewound
+        return {'state': self._state_buf.clone(), 'steps': self.steps,   # _seq is never rewound
                 'alive_known': self._any_alive()}
 
     def restore(self, snap):
         """Rewind to a `snapshot()` of the same episode (device copies only, no host sync)."""
-        live = (self.positions, self.directions, self.speeds, self._alive, self._finishes, self.scores)
-        for dst, src in zip(live, snap['tensors']):
-            dst.copy_(src, non_blocking=True)
+        self._state_buf.copy_(snap['state'], non_blocking=True)
         self.steps = snap['steps']
         self._alive_known = snap['alive_known']
 
