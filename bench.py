@@ -3,29 +3,37 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one launch of the fused step kernel over one batch of config 2 of BASELINE.json
-(4096 synthetic generator-like tracks x 2 cars, L = 128, 18 ray sensors) = 8192 env-steps.
-R independent replicas of that batch are stepped round-robin so that the geometry touched between two
-visits of a replica (R x 12.8 MB) exceeds the 126 MB L2 - no L2 flush kernels in the timed region.
-Actions come from a tape recorded (untimed) with a wall-avoiding heuristic driver, resident in HBM; every
-CYCLE steps a replica's car state is rewound to its mid-race snapshot (6 small device copies, inside the
-timed region) and the same tape is replayed, so ~100 % of the cars are alive throughout - dead cars skip
-the ray cast and would inflate the number.  The alive fraction at both ends of the cycle is reported.
+One "step" = every car of one batch of config 2 of BASELINE.json (4096 synthetic generator-like tracks x 2 cars,
+L = 128, 18 ray sensors) advanced by one environment step, its 18-ray observation and reward written = 8192
+env-steps.  Actions come from a tape recorded (untimed) with a wall-avoiding heuristic driver, resident in HBM; a
+batch is rewound to its mid-race snapshot before every block of <= CYCLE steps and the tape replayed, so ~100 % of
+the cars are alive throughout (dead cars skip the ray cast and would inflate the number).
 
-`value`  : device-resident throughput, CUDA events around the K launches (max over ranks); the launches of a
-           cycle are one `Race.rollout` (glg_race_rollout: one kernel per step, consecutive steps chained car by
-           car), and every step writes its observations and rewards (keep_all).
-`e2e`    : the same metric through the public API for host-resident callers (`Race.host_stepper().step`):
-           host actions in, host observations + rewards out EVERY step (H2D, step kernel, D2H as one CUDA graph,
-           one synchronisation per step), inside the timed region.
-`roofline`: algorithmic bytes of one launch (3120 B per track + 145 B per car) over the
-           average launch duration, against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
-`cpu_baseline`: the reference's algorithm on the host cores - the torch-op restatement (same ATen
-           kernels as the reference's IMPL_GPU path on CPU) and, for information, the OpenMP C port.
-`--impl reference`: times only that CPU restatement (the reference itself cannot travel to the GPU box;
-           its C++ helper needs Boost, which this image lacks - DESIGN.md section 7).
+Timed region (`value`, `ms_per_step`, `roofline`): EXACTLY K = --steps steps, issued as ceil(K / CYCLE) calls of
+`Race.rollout` (glg_race_rollout, GLG_ROLLOUT_FUSED: one persistent kernel per call, every step's observations and
+rewards stored), bracketed by barrier + synchronize on both sides and timed with CUDA events on the launching
+stream.  Before the first event the L2 is flushed (a 256 MB device memset, untimed) and consecutive calls rotate
+over --replicas independent batches, so the geometry is read from HBM.  The block is repeated `config.repeats`
+times (each repeat bracketed and flushed the same way); the MEDIAN block time - max over ranks per repeat - is
+reported.  The warm-up runs the identical block (same call shapes, same buffers), at least --warmup steps.
+
+`e2e`    : the same metric through the public API for host-resident callers, host buffers in and out, copies inside
+           the timed region: `Race.host_stepper().step` (one CUDA graph per step: H2D, step kernel, D2H, one
+           synchronisation per step).
+`roofline`: algorithmic bytes (3120 B per track + 145 B per car, per step) x the steps of a launch
+           over the launch duration, against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+`parity` : the production path (fused rollout) against the literal kernel on a slice of the bench batch, every run.
+`cpu_baseline`: the reference's algorithm on the host cores, ALL 4096 tracks (16 environments of 256, the reference's
+           validity check needs 2.7 MB of temporaries per track): the stock reference from baseline/_ref when it is
+           there (tools/make_baseline_ref.py), else the torch-op restatement (oracle/race_oracle.py, same ATen
+           kernels in the same order); and, for information, the OpenMP C port.
+`--impl reference`: times only that CPU arm, same config.
+`extra`  : config 4 (2^20 tracks x 4 cars sharded over the ranks, T = 200, winner statistics all-gathered inside
+           the timed region), config 3 (episode with two LSTM agents: per-step loop vs CUDA graph) and config 5
+           (Pacman step + observation) - informational, N = 1 only for configs 3 and 5.
 """
 import argparse
+import contextlib
 import json
 import os
 import sys
@@ -39,13 +47,16 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 B_TRACKS, P_CARS, L_SEG, O_RAYS = 4096, 2, 128, 18
-REPLICAS = 16   # default of --replicas
-CYCLE = 100
-KEEP_ALL = True      # every step's observations and rewards are kept ([CYCLE,P,B,20] per cycle), not only the last
+REPLICAS = 4     # default of --replicas
+CYCLE = 100      # steps between rewinds of a batch (one call of Race.rollout)
 PREROLL = 100
 SEED = 1234
+FLUSH_BYTES = 256 << 20
 ALGO_BYTES_PER_TRACK = 3 * (L_SEG + 2) * 8        # centre + left + right points, SURVEY.md 8(d)
 ALGO_BYTES_PER_CAR = 145
+CONFIG4_CARS = [(60., 4., 40.), (60., 1., 80.), (80., 2., 60.), (50., 3., 50.)]
+METRIC = 'race env-steps/sec (envs x players)'
+WORKLOAD = ('config2: Race env, 2 players, 4096 synthetic generator-produced tracks, ray-cast sensors')
 
 
 def synthetic_tracks(n, seed):
@@ -120,7 +131,7 @@ class ClockSampler(threading.Thread):
                 for bit, n in names.items():
                     if isinstance(bit, int) and bit and (mask & bit) == bit and 'None' not in n and 'All' not in n:
                         self.reasons.add(n.replace('nvmlClocksEventReason', '').replace('nvmlClocksThrottleReason', ''))
-                time.sleep(0.005)
+                time.sleep(0.002)
         except Exception as e:  # noqa: BLE001
             self.reasons.add('nvml_unavailable:%s' % type(e).__name__)
 
@@ -140,30 +151,100 @@ def measured_peak():
 def ncu_traffic():
     path = os.path.join(ROOT, 'profiles', 'step_kernel_traffic.json')
     if os.path.exists(path):
-        return json.load(open(path)).get('dram_bytes_per_launch')
-    return None
+        return json.load(open(path))
+    return {}
+
+
+@contextlib.contextmanager
+def stdout_to_stderr():
+    """stdout carries ONE JSON line: chatty libraries (NCCL's banner, the reference's import-time prints) write to
+    file descriptor 1, which points at stderr inside this block."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        yield
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
+def median(xs):
+    s = sorted(xs)
+    n = len(s)
+    return s[n // 2] if n % 2 else 0.5 * (s[n // 2 - 1] + s[n // 2])
 
 
 # ------------------------------------------------------------------------------------------------
 # CPU legs (oracle/ as the thing timed is allowed only here: cpu_baseline and --impl reference)
 # ------------------------------------------------------------------------------------------------
-def cpu_torch_port(steps, warmup, n_tracks=256):
-    from oracle import race_oracle as ro
+CPU_CHUNK = 256      # tracks per CPU environment (the reference's validity check materialises [B, 260^2] temporaries)
+
+
+def _stock_reference():
+    """The UNMODIFIED reference `Race` from baseline/_ref (a copy of /root/reference/{games,utils}, made by
+    tools/make_baseline_ref.py, git-ignored), or None.  Its C++ helper needs Boost, which this image lacks: the
+    import falls back to the reference's own torch path (IMPL_GPU), which runs on `device=cpu`."""
+    ref = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.exists(os.path.join(ref, 'games', 'race.py')):
+        return None
+    try:
+        with stdout_to_stderr():
+            sys.path.insert(0, ref)
+            import games as ref_games                                  # noqa: F401  (slow: tries to build the helper)
+            from games.race import Race as RefRace, RaceCar as RefCar
+            sys.path.remove(ref)
+        return RefRace, RefCar
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write('baseline/_ref could not be imported (%r); timing the restatement instead\n' % (e,))
+        return None
+
+
+def cpu_reference_arm(steps, warmup, n_tracks=None, prefer_stock=True):
+    """env-steps/s of the reference's algorithm on the host cores for the bench config: `n_tracks` (default all
+    4096) tracks x 2 cars as environments of CPU_CHUNK tracks, each stepped once per step with the same heuristic
+    driver the GPU tape was recorded with."""
+    n_tracks = B_TRACKS if n_tracks is None else n_tracks
     torch.set_num_threads(os.cpu_count())
-    env = ro.RaceOracle(timeout=40., cars=ro.default_cars(), framerate=1. / 20.)
+    stock = _stock_reference() if prefer_stock else None
     tracks = synthetic_tracks(B_TRACKS, SEED)[:n_tracks]
     gen = torch.Generator().manual_seed(SEED + 1)
-    states, _ = env.reset(tracks)
-    for s in range(warmup):
-        states, _ = env.step(driver_actions(states, gen))
-    t0 = time.perf_counter()
-    for s in range(warmup, warmup + steps):
-        states, _ = env.step(driver_actions(states, gen))
-    dt = time.perf_counter() - t0
+    envs, states = [], []
+    t_reset = time.perf_counter()
+    for lo in range(0, n_tracks, CPU_CHUNK):
+        if stock is not None:
+            RefRace, RefCar = stock
+            env = RefRace(timeout=40., cars=[RefCar(60., 4., 40.), RefCar(60., 1., 80.)], framerate=1. / 20.,
+                          log_history=False, device=torch.device('cpu'))
+        else:
+            from oracle import race_oracle as ro
+            env = ro.RaceOracle(timeout=40., cars=ro.default_cars(), framerate=1. / 20.)
+        with stdout_to_stderr():
+            s, _ = env.reset(tracks[lo:lo + CPU_CHUNK])
+        envs.append(env)
+        states.append(s)
+    t_reset = time.perf_counter() - t_reset
+
+    def step_all():
+        for i, env in enumerate(envs):
+            states[i], _ = env.step(driver_actions(states[i], gen))
+
+    with torch.no_grad():
+        for s in range(warmup):
+            step_all()
+        t0 = time.perf_counter()
+        for s in range(steps):
+            step_all()
+        dt = time.perf_counter() - t0
+    alive = sum(float(e.alive.float().sum()) for e in envs) / (n_tracks * P_CARS)
+    kind = 'reference' if stock is not None else 'port'
+    what = ('stock reference games/race.py (IMPL_GPU path, device=cpu) from baseline/_ref' if stock is not None else
+            'torch-op restatement of games/race.py IMPL_GPU on CPU (oracle/race_oracle.py)')
     return {'value': steps * n_tracks * P_CARS / dt, 'ms_per_step': 1e3 * dt / steps, 'cores': torch.get_num_threads(),
-            'sample': '%d of the %d tracks x %d cars, %d steps after %d warm-up, torch-op restatement of '
-                      'games/race.py IMPL_GPU on CPU' % (n_tracks, B_TRACKS, P_CARS, steps, warmup),
-            'alive_end': float(env.alive.float().mean())}
+            'kind': kind, 'reset_s': t_reset, 'alive_end': alive, 'same_config': n_tracks == B_TRACKS,
+            'sample': '%d of the %d tracks x %d cars (%d environments of %d), %d steps after %d warm-up, %s'
+                      % (n_tracks, B_TRACKS, P_CARS, len(envs), CPU_CHUNK, steps, warmup, what)}
 
 
 def cpu_c_port(steps=10):
@@ -189,14 +270,16 @@ def cpu_c_port(steps=10):
 def run_reference(args, rank):
     if rank != 0:
         return
-    r = cpu_torch_port(args.steps, args.warmup)
-    line = {'impl': 'reference', 'metric': 'race env-steps/sec (envs x players)', 'value': r['value'],
+    r = cpu_reference_arm(args.steps, args.warmup, n_tracks=args.cpu_tracks)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': r['value'],
             'unit': 'env-steps/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'config2: Race env, 2 players, 4096 synthetic generator-produced tracks, '
-                                   'ray-cast sensors (bounded sample per step, see cpu_baseline.sample)'},
-            'cpu_baseline': {'value': r['value'], 'unit': 'env-steps/s', 'cores': r['cores'], 'kind': 'port',
+            'config': {'workload': WORKLOAD + ' (on the host cores)', 'tracks': B_TRACKS, 'players': P_CARS,
+                       'segments': L_SEG, 'rays': O_RAYS, 'same_config': r['same_config'],
+                       'actions': 'heuristic driver (the one the GPU arm\'s tape is recorded with), computed per step',
+                       'alive_fraction_end': r['alive_end'], 'reset_s': r['reset_s']},
+            'cpu_baseline': {'value': r['value'], 'unit': 'env-steps/s', 'cores': r['cores'], 'kind': r['kind'],
                              'sample': r['sample']},
             'e2e': {'value': r['value'], 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
@@ -207,21 +290,158 @@ def run_reference(args, rank):
 # GPU leg
 # ------------------------------------------------------------------------------------------------
 class Replica(object):
-    """One config-2 batch: environment + resident actions + mid-race snapshot."""
+    """One config-2 batch: environment + resident action tape + mid-race snapshot + preallocated outputs."""
 
-    def __init__(self, idx, rank, device, variant):
+    def __init__(self, idx, rank, device, variant, mode):
         from game_level_gan_b200.games import Race, RaceConfig
         self.env = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False,
                         device=device, variant=variant)
         seed = SEED + 1000 * rank + idx
-        self.acts, self.snap, self.alive_end = record_tape(self.env, synthetic_tracks(B_TRACKS, seed), seed + 1, device)
+        self.tracks = synthetic_tracks(B_TRACKS, seed)
+        self.acts, self.snap, self.alive_end = record_tape(self.env, self.tracks, seed + 1, device)
+        self.states = torch.empty((CYCLE, P_CARS, B_TRACKS, O_RAYS + 2), dtype=torch.float32, device=device)
+        self.rewards = torch.empty((CYCLE, P_CARS, B_TRACKS), dtype=torch.float32, device=device)
+        self.mode, self.plans = mode, {}
+
+    def plan(self, n):
+        if n not in self.plans:
+            self.plans[n] = self.env.rollout_plan(self.acts[PREROLL:PREROLL + n], keep_all=True, mode=self.mode,
+                                                  out=(self.states[:n], self.rewards[:n]))
+        return self.plans[n]
 
     def restore(self):
         self.env.restore(self.snap)
 
-    def cycle(self, n):
-        self.restore()
-        self.env.rollout(self.acts[PREROLL:PREROLL + n], keep_all=KEEP_ALL)
+
+def parity_gate(rep, device, tracks_n=256, steps=40):
+    """The production path (fused rollout of the packed kernel) against the literal kernel (every ray x every wall,
+    one launch per step) on the first `tracks_n` tracks of a bench batch, from reset through PREROLL-like driving:
+    every observation, reward and state array compared bit for bit; mismatches are counted, and classified as
+    near-boundary when the two readings differ by less than 1e-4 relative (none are expected: the pruning is exact)."""
+    from game_level_gan_b200.games import Race, RaceConfig
+    tracks = rep.tracks[:tracks_n]
+    acts = rep.acts[:steps, :, :tracks_n].contiguous()
+    a = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False, device=device, variant='fast')
+    b = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False, device=device, variant='brute')
+    sa0, _ = a.reset(tracks)
+    sb0, _ = b.reset(tracks)
+    sa, ra = a.rollout(acts, keep_all=True, mode='fused')
+    sb, rb = b.rollout(acts, keep_all=True, mode='stepwise')
+
+    def diff(x, y):
+        x, y = x.float(), y.float()
+        bad = ~((x == y) | (torch.isnan(x) & torch.isnan(y)))
+        near = bad & ((x - y).abs() <= 1e-4 * torch.maximum(x.abs(), y.abs()).clamp(min=1e-6))
+        return int(bad.sum()), int(near.sum())
+
+    pairs = [(sa0, sb0), (sa, sb), (ra, rb), (a.positions, b.positions), (a.directions, b.directions),
+             (a.speeds, b.speeds), (a.scores, b.scores), (a.alive, b.alive), (a.finishes, b.finishes),
+             (a.winners(), b.winners())]
+    bad = near = 0
+    for x, y in pairs:
+        d = diff(x, y)
+        bad += d[0]
+        near += d[1]
+    return {'car_steps_checked': (steps + 1) * tracks_n * P_CARS, 'values_compared': int(sum(x.numel() for x, _ in pairs)),
+            'mismatches': bad, 'near_boundary': near,
+            'against': 'literal kernel (GLG_STEP_BRUTE, one launch per step) on the first %d tracks of a bench batch, '
+                       'reset + %d driver steps' % (tracks_n, steps)}
+
+
+def run_config4(args, rank, world, device, barrier, total_tracks, trials=4, T=200):
+    """Config 4 of BASELINE.json: 2^20 iid-9 tracks x 4 cars sharded over the ranks by board (all `trials` repetitions
+    of a board on one rank, train-gan.py:84), tracks and forward-biased random actions generated ON DEVICE per rank
+    (seed + rank), one fused rollout of T = 200 steps, then the per-board winner statistics
+    (train-gan.py:103-104) all-gathered - rollout, statistics and collective inside the timed region."""
+    import torch.distributed as dist
+    from game_level_gan_b200 import dist as gdist
+    from game_level_gan_b200.games import Race, RaceCar
+    boards = total_tracks // trials
+    lo, hi = gdist.shard_bounds(boards, rank, world)
+    bl = hi - lo
+    B = bl * trials
+    P = len(CONFIG4_CARS)
+    gen = torch.Generator(device=device).manual_seed(SEED + 4000 + rank)
+    levels = torch.randint(0, 9, (bl, L_SEG), generator=gen, device=device, dtype=torch.uint8)
+    levels = levels.repeat(trials, 1)                                    # trial-major
+    env = Race(timeout=40., cars=[RaceCar(*c) for c in CONFIG4_CARS], framerate=1. / 20., log_history=False, device=device,
+               variant=args.variant)
+    t0 = time.perf_counter()
+    env.reset_levels(levels)
+    torch.cuda.synchronize()
+    reset_s = time.perf_counter() - t0
+    snap = env.snapshot()
+    acts = torch.randint(0, 9, (T, P, B), generator=gen, device=device)
+    fwd = torch.rand((T, P, B), generator=gen, device=device) < 0.6
+    acts[fwd] = 1
+    del fwd
+    plan = env.rollout_plan(acts, keep_all=False, mode=args.rollout_mode)
+    gather = gdist.ShardGather(boards, (P + 1,), torch.float32, device)
+    times = []
+    for rep in range(3):                                                  # the first repetition is the warm-up
+        env.restore(snap)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        plan.run()
+        stats = gather(env.winner_stats(trials))
+        e1.record()
+        barrier()
+        times.append(e0.elapsed_time(e1))
+    tm = torch.tensor(times[1:], device=device)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms = float(tm.min())
+    fin = gdist.finish_rate(env.finishes)
+    alive = float(env.alive.float().mean())
+    out = {'workload': 'config4: Race env, 4 players, %d tracks (%d boards x %d trials) sharded over %d GPU(s), T = %d, '
+                       'NCCL all-gather of the per-board winner statistics inside the timed region' % (total_tracks, boards, trials, world, T),
+           'value': total_tracks * P * T / (ms * 1e-3), 'unit': 'env-steps/s', 'ms': ms, 'tracks_per_gpu': B,
+           'reset_s_rank0': reset_s, 'alive_fraction_end_rank0': alive, 'finish_rate': fin,
+           'stats_rows': int(stats.size(0)), 'stats_sum': float(stats.sum()),
+           'gathered_bytes': int(stats.numel() * 4), 'launches': plan.launches + 2 + (1 if world > 1 else 0),
+           'roofline_frac': (ALGO_BYTES_PER_TRACK + ALGO_BYTES_PER_CAR * P) * B * T / (ms * 1e-3) / (measured_peak()[0] * 1e9),
+           'note': 'forward-biased random actions: cars die (dead cars skip the ray cast), see alive_fraction_end'}
+    del plan, acts, env
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_config5(device, T=100):
+    """Config 5: Pacman, 65 536 boards of 15x15, 2 players, random actions: step + observation per step."""
+    import numpy as np
+    from game_level_gan_b200.games import Pacman
+    B, H, W, P = 65536, 15, 15, 2
+    rng = np.random.default_rng(5)
+    fields = rng.choice(4, size=(B, H, W), p=[0.4, 0.5, 0.07, 0.03])          # generators/pacman_generator.py:56
+    board = np.zeros((B, H, W, 4 + P), dtype=np.int32)
+    np.put_along_axis(board[..., :4], fields[..., None], 1, axis=-1)
+    for p, (x, y) in enumerate(((0, 0), (H - 1, W - 1))):                       # :63 opposite corners
+        board[:, x, y, :] = 0
+        board[:, x, y, 0] = 1
+        board[:, x, y, 4 + p] = 1
+    env = Pacman((H, W), P, batch_size=B, device=device)
+    env.reset_device(torch.from_numpy(board).to(device))
+    acts = torch.randint(0, 5, (T, B, P), dtype=torch.int32, device=device)
+    for t in range(10):
+        env.step_device(acts[t])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(T):
+        env.step_device(acts[t])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / T
+    obs_bytes = P * B * H * W * (4 + 2 * P) * 4
+    grid_bytes = 2 * B * H * W * (4 + P) * 4
+    peak = measured_peak()[0]
+    return {'workload': 'config5: Pacman %d boards of %dx%d, %d players, step + observation kernels' % (B, H, W, P),
+            'us_per_step': 1e3 * ms, 'board_steps_per_s': B / (ms * 1e-3),
+            'bytes_per_step': obs_bytes + grid_bytes,
+            'roofline': {'bound': 'hbm', 'achieved': (obs_bytes + grid_bytes) / (ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                         'frac': (obs_bytes + grid_bytes) / (ms * 1e-3) / 1e9 / peak,
+                         'note': 'whole step (3 kernels); observation write P*B*H*W*(4+2P)*4 B + grid read and write'}}
 
 
 def run_b200(args, rank, world):
@@ -230,19 +450,10 @@ def run_b200(args, rank, world):
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
     if world > 1:
-        # stdout carries ONE JSON line: NCCL prints its version banner to stdout when the communicator is created,
-        # so file descriptor 1 points at stderr until the first collective has run
-        sys.stdout.flush()
-        saved_stdout = os.dup(1)
-        os.dup2(2, 1)
-        try:
+        with stdout_to_stderr():
             dist.init_process_group('nccl', device_id=device)
             dist.barrier()
             torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved_stdout, 1)
-            os.close(saved_stdout)
     import __graft_entry__ as entry
     if rank == 0:
         entry.build()
@@ -254,49 +465,80 @@ def run_b200(args, rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    REPLICAS = args.replicas
-    reps = [Replica(i, rank, device, args.variant) for i in range(REPLICAS)]
+    from game_level_gan_b200 import dist as gdist
+    R = max(1, args.replicas)
+    reps = [Replica(i, rank, device, args.variant, args.rollout_mode) for i in range(R)]
     alive_start = float(torch.stack([r.env.alive.float().mean() for r in reps]).mean())     # envs sit at their snapshots
+    K = args.steps
+    chunks = [CYCLE] * (K // CYCLE) + ([K % CYCLE] if K % CYCLE else [])
+    flush = torch.empty((FLUSH_BYTES,), dtype=torch.uint8, device=device)
+    gather = gdist.ShardGather(world * B_TRACKS, (), torch.int8, device) if world > 1 else None
+    launches = [0]
 
-    def run_steps(k):
-        done, i = 0, 0
-        while done < k:
-            n = min(CYCLE, k - done)
-            reps[i % REPLICAS].cycle(n)
-            done += n
-            i += 1
+    def block(first):
+        """K steps; call j replays the tape of batch (first + j) % R from its snapshot.  The rewind of the first
+        batch is done by the caller before the first event."""
+        n_launch = 0
+        for j, n in enumerate(chunks):
+            rep = reps[(first + j) % R]
+            if j:
+                rep.restore()
+            rep.plan(n).run()
+            n_launch += rep.plan(n).launches
+            if gather is not None and n == CYCLE:     # the one collective of the path, once per episode (SURVEY.md 8(e))
+                gather(rep.env.winners())
+                n_launch += 3
+        launches[0] = n_launch
 
-    run_steps(max(args.warmup, 3))
-    if world > 1:       # warm-up of the collective too (communicator set-up is not part of a step)
-        from game_level_gan_b200 import dist as gdist
-        gdist.all_gather_winners(reps[0].env.winners())
-    barrier()
+    def timed_block(first):
+        barrier()
+        reps[first % R].restore()
+        flush.zero_()                                  # L2 flush (untimed); also keeps the GPU busy while the host enqueues
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        block(first)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
+    # warm-up: the identical block (same call shapes, same buffers), at least --warmup steps and every batch once
+    n_warm = max(R, -(-max(args.warmup, 3) // max(K, 1)))
+    for i in range(n_warm):
+        timed_block(i)
+    repeats = args.repeats if args.repeats > 0 else max(3, min(15, 6000 // max(K, 1)))
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.05)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    run_steps(args.steps)
-    if world > 1:       # the one collective of the path: winners of every shard
-        from game_level_gan_b200 import dist as gdist
-        gdist.all_gather_winners(reps[0].env.winners())
-    e1.record()
-    barrier()
+    times = [timed_block(i) for i in range(repeats)]
     sampler.stop_flag = True
-    ms = e0.elapsed_time(e1)
-    alive_end = sum(r.alive_end for r in reps) / len(reps)     # at the end of a full CYCLE of the tape
+    tm = torch.tensor(times, device=device, dtype=torch.float64)
     if world > 1:
-        tm = torch.tensor([ms], device=device)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ms = float(tm.item())
+    times = [float(x) for x in tm.tolist()]
+    ms = median(times)
+    alive_end = sum(r.alive_end for r in reps) / len(reps)     # at the end of a full CYCLE of the tape
     sampler.join(timeout=2)
-    env_steps = args.steps * B_TRACKS * P_CARS
+    env_steps = K * B_TRACKS * P_CARS
     value = world * env_steps / (ms * 1e-3)
+
+    # a lone collective, for the record (N > 1): what one episode end costs
+    collective_us = None
+    if gather is not None:
+        w = reps[0].env.winners()
+        for i in range(3):
+            gather(w)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(10):
+            gather(w)
+        e1.record()
+        barrier()
+        collective_us = 1e3 * e0.elapsed_time(e1) / 10
 
     # ---- end-to-end through the public API with host buffers ----
     from game_level_gan_b200.games import Race, RaceConfig
-    e2e_steps = min(args.steps, 400)
+    e2e_steps = min(max(K, 200), 1000)
     env = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False, device=device,
                variant=args.variant)
     tape, snap, _ = record_tape(env, synthetic_tracks(B_TRACKS, SEED + 77 + rank), SEED + 78 + rank, device)
@@ -321,52 +563,77 @@ def run_b200(args, rank, world):
     barrier()
     e2e_ms = t0.elapsed_time(t1)
     if world > 1:
-        tm = torch.tensor([e2e_ms], device=device)
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tm.item())
+        tmx = torch.tensor([e2e_ms], device=device)
+        dist.all_reduce(tmx, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tmx.item())
     e2e_value = world * e2e_steps * B_TRACKS * P_CARS / (e2e_ms * 1e-3)
 
+    extra = {}
+    if not args.no_extra:
+        extra['config4'] = run_config4(args, rank, world, device, barrier, args.config4_tracks)
+    parity = parity_gate(reps[0], device) if rank == 0 else None
     if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
+    if world == 1 and not args.no_extra:
+        extra['config5'] = run_config5(device)
+        extra['config3'] = run_rollout_workload(args, quiet=True)
     peak, peak_kind = measured_peak()
-    algo_bytes = ALGO_BYTES_PER_TRACK * B_TRACKS + ALGO_BYTES_PER_CAR * B_TRACKS * P_CARS
-    launch_ms = ms / args.steps
-    achieved = algo_bytes / (launch_ms * 1e-3) / 1e9
+    algo_step = ALGO_BYTES_PER_TRACK * B_TRACKS + ALGO_BYTES_PER_CAR * B_TRACKS * P_CARS
+    step_ms = ms / K
+    n_calls = len(chunks)
+    achieved = algo_step / (step_ms * 1e-3) / 1e9
+    traffic = ncu_traffic()
+    fused = reps[0].plan(chunks[0]).launches == 1
     line = {
-        'metric': 'race env-steps/sec (envs x players)', 'value': value, 'unit': 'env-steps/s',
-        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': launch_ms,
+        'metric': METRIC, 'value': value, 'unit': 'env-steps/s',
+        'n_gpus': world, 'steps': K, 'warmup': args.warmup, 'ms_per_step': step_ms,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'config2: Race env, 2 players, 4096 synthetic generator-produced tracks, '
-                               'ray-cast sensors, per GPU', 'tracks': B_TRACKS, 'players': P_CARS,
-                   'segments': L_SEG, 'rays': O_RAYS, 'kernel_variant': args.variant,
-                   'l2': '%d replicas stepped round-robin, %.0f MB of geometry > 126 MB L2 (no flush)'
-                         % (REPLICAS, REPLICAS * ALGO_BYTES_PER_TRACK * B_TRACKS / 1e6),
+        'config': {'workload': WORKLOAD + ', per GPU', 'tracks': B_TRACKS, 'players': P_CARS,
+                   'segments': L_SEG, 'rays': O_RAYS, 'kernel_variant': args.variant, 'rollout_mode': args.rollout_mode,
+                   'repeats': repeats, 'block_ms': times, 'block_ms_median': ms, 'warmup_blocks': n_warm,
+                   'l2': 'flushed before every timed block (%d MB device memset, untimed); calls of a block rotate over %d '
+                         'independent batches (%.0f MB of geometry each)' % (FLUSH_BYTES >> 20, R, ALGO_BYTES_PER_TRACK * B_TRACKS / 1e6),
                    'alive_fraction': [alive_start, alive_end],
-                   'launches': 'one step kernel per step (glg_race_rollout: chained car by car, every step writes its '
-                               'observations and rewards, keep_all=%s)' % KEEP_ALL,
-                   'state_restore_every_steps': CYCLE, 'actions': 'heuristic-driver tape, race steps %d-%d' % (PREROLL, PREROLL + CYCLE), 'parallelism': 'dp%d (tracks sharded)' % world},
+                   'launches': ('%d call(s) of Race.rollout per block of %d steps; ' % (n_calls, K)) +
+                               ('one persistent kernel per call (glg_race_rollout, GLG_ROLLOUT_FUSED: track records stay in shared '
+                                'memory, car state in registers); ' if fused else 'one step kernel per step; ') +
+                               'every step writes its observations and rewards (keep_all)',
+                   'state_restore_every_steps': CYCLE, 'actions': 'heuristic-driver tape, race steps %d-%d' % (PREROLL, PREROLL + CYCLE),
+                   'collective': None if world == 1 else
+                       'all-gather of the winners (int8) at every episode end, i.e. after every full %d-step call '
+                       '(%d in a block of %d steps); a lone one takes %.1f us' % (CYCLE, K // CYCLE, K, collective_us),
+                   'parallelism': 'dp%d (tracks sharded)' % world},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': ncu_traffic(), 'peak_source': peak_kind,
-                     'algorithmic_bytes_per_launch': algo_bytes},
+                     'traffic': traffic.get('dram_bytes_per_launch'), 'traffic_note': traffic.get('note'), 'peak_source': peak_kind,
+                     'algorithmic_bytes_per_step': algo_step,
+                     'algorithmic_bytes_per_launch': algo_step * chunks[0] if fused else algo_step,
+                     'steps_per_launch': chunks[0] if fused else 1,
+                     'launch_ms': ms / n_calls if fused else step_ms},
         'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'steps': e2e_steps,
                 'api': 'Race.host_stepper().step(host actions) -> host observations, rewards (one CUDA graph per step)',
-                'h2d_bytes_per_step': P_CARS * B_TRACKS * 8 + 12,
+                'h2d_bytes_per_step': P_CARS * B_TRACKS * 8 + 16,
                 'd2h_bytes_per_step': P_CARS * B_TRACKS * (O_RAYS + 2 + 1) * 4 + 4096},
-        'gpu_launches': args.steps, 'clocks': sampler.summary(),
+        'gpu_launches': launches[0], 'clocks': sampler.summary(), 'parity': parity, 'extra': extra,
     }
+    if value < e2e_value:
+        line['sanity'] = 'device-resident value below the host round-trip value: the timed region is not steady state'
     if world == 1 and not args.no_cpu:
-        tp = cpu_torch_port(steps=20, warmup=3)
+        tp = cpu_reference_arm(steps=3, warmup=1, n_tracks=args.cpu_tracks)
         cp = cpu_c_port()
-        line['cpu_baseline'] = {'value': tp['value'], 'unit': 'env-steps/s', 'cores': tp['cores'], 'kind': 'port',
+        line['cpu_baseline'] = {'value': tp['value'], 'unit': 'env-steps/s', 'cores': tp['cores'], 'kind': tp['kind'],
                                 'sample': tp['sample'], 'c_port_value': cp['value'], 'c_port_cores': cp['cores'],
                                 'c_port_sample': 'all 4096 tracks x 2 cars, 10 steps, oracle/race_oracle.c (OpenMP)'}
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------
-# config 3: whole-episode rollout with recurrent policies (informational, `--workload rollout`)
+# config 3: whole-episode rollout with recurrent policies (informational; also `--workload rollout`)
 # ------------------------------------------------------------------------------------------------
 class LstmAgents(object):
     """P independent LSTMPolicy(20, 9)-shaped networks (policies/LSTMPolicy.py:6-41: two LSTMCell(256) + linear
@@ -399,12 +666,11 @@ class LstmAgents(object):
         return torch.stack(acts, 0)
 
 
-def run_rollout_workload(args):
+def run_rollout_workload(args, quiet=False):
     """train-gan.py:86-104 on synthetic boards: reset, play the episode with 2 LSTM agents, winner statistics.
-    Prints one JSON line comparing the reference-style per-step loop with GraphedRollout."""
+    Compares the reference-style per-step loop with GraphedRollout."""
     from game_level_gan_b200.games import GraphedRollout, Race, RaceConfig
-    device = torch.device('cuda', 0)
-    torch.cuda.set_device(0)
+    device = torch.device('cuda', torch.cuda.current_device())
     B, T_limit = 2060, 500                                          # (1024 generated + 6 predefined) x 2 mirrored
     tracks = synthetic_tracks(B, SEED)
     out = {'workload': 'config3: episode rollout, %d boards x 2 LSTM(256x2) agents, <= %d steps' % (B, T_limit)}
@@ -413,7 +679,7 @@ def run_rollout_workload(args):
             env = Race(timeout=T_limit / 20. - 0.025, cars=RaceConfig.cars, framerate=1. / 20., log_history=False, device=device)
             agents = LstmAgents(2, B, device)
             best = None
-            for rep in range(3):
+            for rep in range(2 if quiet else 3):
                 states, any_valid = env.reset(tracks)
                 agents.reset()
                 roll = GraphedRollout(env, agents, steps_per_replay=16, on_reset=agents.reset).capture() if mode == 'graph' else None
@@ -430,21 +696,28 @@ def run_rollout_workload(args):
                 best = dt if best is None else min(best, dt)
             out[mode] = {'episode_ms': 1e3 * best, 'steps': env.steps, 'us_per_step': 1e6 * best / max(env.steps - 1, 1),
                          'env_steps_per_s': (env.steps - 1) * B * 2 / best, 'finished_frac': float(env.finishes.float().mean())}
-    print(json.dumps(out), flush=True)
+    if not quiet:
+        print(json.dumps(out), flush=True)
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20000)
-    ap.add_argument('--warmup', type=int, default=200)
+    ap.add_argument('--steps', type=int, default=2000)
+    ap.add_argument('--warmup', type=int, default=100)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--variant', default='fast', choices=['fast', 'warp', 'scan', 'brute'])
+    ap.add_argument('--rollout-mode', default='fused', choices=['fused', 'chained', 'stepwise'])
+    ap.add_argument('--repeats', type=int, default=0, help='timed blocks (0 = 3..15 depending on --steps); the median is reported')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
-    ap.add_argument('--replicas', type=int, default=REPLICAS, help='independent config-2 batches stepped round-robin')
+    ap.add_argument('--no-extra', action='store_true', help='skip the config 3 / 4 / 5 records')
+    ap.add_argument('--replicas', type=int, default=REPLICAS, help='independent config-2 batches the calls of a block rotate over')
     ap.add_argument('--tracks', type=int, default=4096, help='tracks per batch (default = config 2)')
+    ap.add_argument('--cpu-tracks', type=int, default=None, help='tracks of the CPU arm (default: all, = same config)')
+    ap.add_argument('--config4-tracks', type=int, default=1 << 20, help='tracks of the config-4 record over all ranks')
     ap.add_argument('--workload', default='step', choices=['step', 'rollout'],
-                    help="'rollout': config 3 (episode with LSTM agents), informational, not the contract line")
+                    help="'rollout': config 3 alone (episode with LSTM agents), informational, not the contract line")
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -453,11 +726,11 @@ def main():
         if rank == 0:
             import __graft_entry__ as entry
             entry.build()
+            torch.cuda.set_device(0)
             run_rollout_workload(args)
         return
     if args.impl == 'reference':
-        if args.steps > 400:
-            args.steps = 200          # bounded: ~0.1 s per sampled step on the host
+        args.steps = min(args.steps, 200)          # bounded: ~0.5 s per step of all 4096 tracks on the host
         args.warmup = min(args.warmup, 5)
         run_reference(args, rank)
         return

@@ -13,7 +13,8 @@ MAX_PLAYERS = 8
 MAX_RAYS = 32
 ALIVE_SLOTS = 1024
 STEP_FAST, STEP_BRUTE, STEP_SCAN, STEP_PACKED = 0, 1, 2, 3
-ABI_VERSION = 6
+ROLLOUT_STEPWISE, ROLLOUT_CHAINED, ROLLOUT_FUSED = 0, 1, 2
+ABI_VERSION = 7
 
 
 class GlgError(RuntimeError):
@@ -53,7 +54,7 @@ SYMBOLS = {
     'glg_race_step': (ctypes.c_int, [ctypes.POINTER(RaceParams), _vp, _i32, _i32, _vp, _vp, _vp, RaceState,
                                      _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp]),
     'glg_race_rollout': (ctypes.c_int, [ctypes.POINTER(RaceParams), _vp, _i32, _i32, _vp, _i32, _vp, _vp,
-                                        RaceState, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _vp]),
+                                        RaceState, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp]),
     'glg_race_chain_bytes': (_i64, [_i32, _i32]),
     'glg_race_winners': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     'glg_winner_stats': (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),

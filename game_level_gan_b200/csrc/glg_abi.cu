@@ -27,4 +27,4 @@ int launch_status(const char* what)
 }  // namespace glg
 
 extern "C" const char* glg_last_error(void) { return glg::g_error; }
-extern "C" int glg_abi_version(void) { return 6; }
+extern "C" int glg_abi_version(void) { return 7; }

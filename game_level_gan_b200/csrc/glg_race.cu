@@ -14,6 +14,8 @@
 // kinematics, progress arg-min, wall/finish collision, reward/score, and the ray-cast sensors for
 // its car with the lanes striding over points / walls, and packs the [P,B,O+2] observation.
 // There is no cross-car dependence in the reference step, so no global sync.
+#include <stdlib.h>
+
 #include "glg_common.cuh"
 #include "glg_exact.cuh"
 #include "glg_sensors.cuh"
@@ -371,21 +373,37 @@ static int check_step_args(const glg_race_params* pr, const float* geom, int B, 
     return GLG_OK;
 }
 
+// Programmatic dependent launch is requested for every step launch, also while the stream is being captured (the
+// capture records a programmatic dependency edge, so graph replays keep the overlap of consecutive steps);
+// GLG_GRAPH_PDL=0 in the environment falls back to plain stream order inside captured graphs.
+static bool pdl_allowed(cudaStream_t stream)
+{
+    static const int graph_pdl = [] { const char* e = getenv("GLG_GRAPH_PDL"); return (e && e[0] == '0') ? 0 : 1; }();
+    if (graph_pdl) return true;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cap);
+    return cap == cudaStreamCaptureStatusNone;
+}
+
 template <int VARIANT, int OC>
-static void launch_one(const glg_race_params* pr, const StepArgs& a, cudaStream_t stream)
+static void launch_one(const glg_race_params* pr, const StepArgs& a, bool pdl, cudaStream_t stream)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(a.B);
     cfg.blockDim = dim3(32 * pr->num_players);
     cfg.dynamicSmemBytes = smem_total(a.N, pr->num_players);
     cfg.stream = stream;
+    // long tracks with many cars need more than the default 48 KB of dynamic shared memory: opt in per instantiation
+    static size_t smem_opted = 48 * 1024;
+    if (cfg.dynamicSmemBytes > smem_opted) {
+        cudaFuncSetAttribute(race_step_kernel<VARIANT, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+        smem_opted = cfg.dynamicSmemBytes;
+    }
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see griddepcontrol in the kernel
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(stream, &cap);
     cfg.attrs = attr;
-    cfg.numAttrs = cap == cudaStreamCaptureStatusNone ? 1 : 0;         // plain stream order inside a captured graph
+    cfg.numAttrs = pdl ? 1 : 0;
     cudaLaunchKernelEx(&cfg, race_step_kernel<VARIANT, OC>, *pr, a);
 }
 
@@ -401,7 +419,7 @@ static int effective_variant(const glg_race_params* pr, const float* geom, int N
 }
 
 template <int TPB>
-static void launch_packed(const glg_race_params* pr, const StepArgs& a, cudaStream_t stream)
+static void launch_packed(const glg_race_params* pr, const StepArgs& a, bool pdl, cudaStream_t stream)
 {
     const int WPT = (pr->num_players + 1) / 2;
     cudaLaunchConfig_t cfg = {};
@@ -415,28 +433,65 @@ static void launch_packed(const glg_race_params* pr, const StepArgs& a, cudaStre
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(stream, &cap);
     cfg.attrs = attr;
-    cfg.numAttrs = cap == cudaStreamCaptureStatusNone ? 1 : 0;
+    cfg.numAttrs = pdl ? 1 : 0;
     StepArgs ap = a;
     ap.pk = pk_layout(a.N, 2 * WPT);
     cudaLaunchKernelEx(&cfg, race_step_packed_kernel<TPB>, *pr, ap);
 }
 
-static int launch_step(const glg_race_params* pr, const StepArgs& a, int variant, cudaStream_t stream)
+// `variant` is the effective one (effective_variant); `pdl` from pdl_allowed, once per API call
+static int launch_step(const glg_race_params* pr, const StepArgs& a, int variant, bool pdl, cudaStream_t stream)
 {
-    variant = effective_variant(pr, a.geom, a.N, variant);
     if (variant == GLG_STEP_PACKED) {
-        if (pr->num_players <= 2) launch_packed<2>(pr, a, stream);
-        else launch_packed<1>(pr, a, stream);
+        if (pr->num_players <= 2) launch_packed<2>(pr, a, pdl, stream);
+        else launch_packed<1>(pr, a, pdl, stream);
         return GLG_OK;
     }
-    if (variant == GLG_STEP_BRUTE) launch_one<GLG_STEP_BRUTE, 0>(pr, a, stream);
-    else if (variant == GLG_STEP_FAST) launch_one<GLG_STEP_FAST, 18>(pr, a, stream);
-    else if (pr->num_rays == 18) launch_one<GLG_STEP_SCAN, 18>(pr, a, stream);
-    else launch_one<GLG_STEP_SCAN, 0>(pr, a, stream);
+    if (variant == GLG_STEP_BRUTE) launch_one<GLG_STEP_BRUTE, 0>(pr, a, pdl, stream);
+    else if (variant == GLG_STEP_FAST) launch_one<GLG_STEP_FAST, 18>(pr, a, pdl, stream);
+    else if (pr->num_rays == 18) launch_one<GLG_STEP_SCAN, 18>(pr, a, pdl, stream);
+    else launch_one<GLG_STEP_SCAN, 0>(pr, a, pdl, stream);
     return GLG_OK;
+}
+
+}  // namespace glg
+
+#include "glg_race_fused.cuh"
+
+namespace glg {
+
+// GLG_ROLLOUT_FUSED: one persistent launch for all T steps (configurations GLG_STEP_PACKED covers)
+static void launch_fused_rollout(const glg_race_params* pr, const float* geom, int B, int N, const int64_t* actions, int T,
+                                 const uint8_t* valid, const float* extent, const glg_race_state& st, int first_step_no,
+                                 float* states_out, float* rewards_out, int keep_all, int32_t* alive_stamp,
+                                 int first_launch_seq, float* history, int record_id, bool pdl, cudaStream_t stream)
+{
+    const int P = pr->num_players;
+    const int WPT = (P + 1) / 2;
+    const int TPB = P <= 2 ? 2 : 1;
+    FusedArgs a{geom, actions, valid, extent, st, states_out, rewards_out, alive_stamp, history,
+                B, N, T, first_step_no, history ? record_id : -1, first_launch_seq + T - 1, keep_all ? 1 : 0,
+                0, 0, 0, 0, 0, 0};
+    fused_layout(a, N, 2 * WPT);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((B + TPB - 1) / TPB);
+    cfg.blockDim = dim3(32 * WPT * TPB);
+    cfg.dynamicSmemBytes = (size_t)TPB * a.track_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    static size_t smem_opted[2] = {48 * 1024, 48 * 1024};
+    if (cfg.dynamicSmemBytes > smem_opted[TPB - 1]) {
+        if (TPB == 2) cudaFuncSetAttribute(race_rollout_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+        else cudaFuncSetAttribute(race_rollout_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+        smem_opted[TPB - 1] = cfg.dynamicSmemBytes;
+    }
+    if (TPB == 2) cudaLaunchKernelEx(&cfg, race_rollout_fused_kernel<2>, *pr, a);
+    else cudaLaunchKernelEx(&cfg, race_rollout_fused_kernel<1>, *pr, a);
 }
 
 }  // namespace glg
@@ -480,7 +535,7 @@ extern "C" int glg_race_step(const glg_race_params* params, const float* geom, i
     if (rc != GLG_OK || B == 0) return rc;
     StepArgs a{geom, actions, valid, extent, state, states_out, rewards_out, alive_stamp, history, nullptr, base,
                B, N, step_no, record_id, launch_seq, 0, 0, {}, nullptr, 0, 0, 1};
-    launch_step(params, a, variant, (cudaStream_t)stream);
+    launch_step(params, a, effective_variant(params, geom, N, variant), pdl_allowed((cudaStream_t)stream), (cudaStream_t)stream);
     return launch_status("glg_race_step");
 }
 
@@ -489,24 +544,40 @@ extern "C" int glg_race_rollout(const glg_race_params* params, const float* geom
                                 glg_race_state state,
                                 int32_t first_step_no, float* states_out, float* rewards_out, int32_t keep_all,
                                 int32_t* alive_stamp, int32_t first_launch_seq, int32_t* chain,
+                                float* history, int32_t record_id, int32_t mode,
                                 int32_t variant, glg_stream_t stream)
 {
     using namespace glg;
     const int rc = check_step_args(params, geom, B, N, actions, valid, extent, variant, state, states_out, rewards_out);
     if (rc != GLG_OK || B == 0 || T <= 0) return rc;
+    GLG_REQUIRE(mode == GLG_ROLLOUT_STEPWISE || mode == GLG_ROLLOUT_CHAINED || mode == GLG_ROLLOUT_FUSED,
+                "glg_race_rollout: unknown mode %d", mode);
+    GLG_REQUIRE(mode != GLG_ROLLOUT_CHAINED || chain != nullptr, "glg_race_rollout: GLG_ROLLOUT_CHAINED needs the chain scratch");
     const size_t PB = (size_t)params->num_players * B;
     const size_t W = params->num_rays + 2;
+    const int eff = effective_variant(params, geom, N, variant);
+    const bool pdl = pdl_allowed((cudaStream_t)stream);
+    if (mode == GLG_ROLLOUT_FUSED) {
+        if (eff == GLG_STEP_PACKED) {
+            launch_fused_rollout(params, geom, B, N, actions, T, valid, extent, state, first_step_no, states_out,
+                                 rewards_out, keep_all, alive_stamp, first_launch_seq, history, record_id, pdl,
+                                 (cudaStream_t)stream);
+            return launch_status("glg_race_rollout");
+        }
+        mode = chain ? GLG_ROLLOUT_CHAINED : GLG_ROLLOUT_STEPWISE;   // configurations the fused kernel does not cover
+    }
+    if (mode == GLG_ROLLOUT_STEPWISE) chain = nullptr;
     // LL hand-over (packed kernel, every step has its own output buffer): see glg_race_packed.cuh
-    const bool ll = chain != nullptr && keep_all && effective_variant(params, geom, N, variant) == GLG_STEP_PACKED;
+    const bool ll = chain != nullptr && keep_all && eff == GLG_STEP_PACKED;
     unsigned long long* llw = chain ? reinterpret_cast<unsigned long long*>(chain + ((PB + 3) & ~(size_t)3)) : nullptr;
     for (int t = 0; t < T; ++t) {
         StepArgs a{geom, actions + (size_t)t * PB, valid, extent, state,
                    keep_all ? states_out + (size_t)t * PB * W : states_out,
                    keep_all ? rewards_out + (size_t)t * PB : rewards_out,
-                   alive_stamp, nullptr, chain, nullptr, B, N, first_step_no + t, -1, first_launch_seq + t,
+                   alive_stamp, history, chain, nullptr, B, N, first_step_no + t, history ? record_id : -1, first_launch_seq + t,
                    (chain != nullptr && t > 0) ? 1 : 0, keep_all ? 1 : 0, {}, llw,
                    (ll && t > 0) ? 1 : 0, (ll && t < T - 1) ? 1 : 0, (!ll || t == T - 1) ? 1 : 0};
-        launch_step(params, a, variant, (cudaStream_t)stream);
+        launch_step(params, a, eff, pdl, (cudaStream_t)stream);
     }
     return launch_status("glg_race_rollout");
 }

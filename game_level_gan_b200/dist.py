@@ -2,9 +2,13 @@
 
 Tracks are fully independent (no cross-track term in reset/step/winners), so every
 rank steps its own contiguous block of boards with no data-path communication.  The only exchange is
-the all-gather of the per-track winners (and, optionally, the finish counts) that the winner
-discriminator consumes after an episode (train-gan.py:98, 103-105).  Works with the `nccl` backend
-on GPUs (NVLink / NVSwitch) and with `gloo` on CPU tensors (tests).
+the all-gather of the per-track winners / per-board winner statistics that the winner discriminator
+consumes after an episode (train-gan.py:98, 103-105).  Works with the `nccl` backend on GPUs
+(NVLink / NVSwitch) and with `gloo` on CPU tensors (tests).
+
+Shard sizes follow from `shard_bounds` on every rank, so nothing about sizes is communicated and the
+gather never synchronises with the host: one `all_gather_into_tensor` on buffers that a `ShardGather`
+allocates once (shards padded to the largest, the padding dropped by a fixed index on the way out).
 """
 import torch
 import torch.distributed as dist
@@ -27,43 +31,69 @@ def shard_trial_major(tracks, trials, rank, world):
     return local.reshape(trials * (hi - lo), *tracks.shape[1:]).contiguous(), (lo, hi)
 
 
-def all_gather_winners(winners, group=None):
-    """winners [b_local] int64 of every rank -> [sum b_local] on every rank, in rank order.
+def _world(group):
+    return dist.get_world_size(group) if dist.is_initialized() else 1
 
-    On the wire the winners travel as int8 (values -1..P-1), 1 byte per track: 1 MB for 2^20 tracks,
-    i.e. latency-bound on NVLink; shards may have different sizes (padded to the largest)."""
-    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+
+class ShardGather(object):
+    """All-gather of per-board rows ([boards_local, *row] on every rank -> [boards, *row] in rank order) for a FIXED
+    sharding of `total` boards by `shard_bounds`.  Buffers are allocated once; `__call__` is one collective and two
+    device copies, no host synchronisation - safe inside a timed region or a CUDA graph."""
+
+    def __init__(self, total, row_shape, dtype, device, group=None):
+        self.group, self.total = group, int(total)
+        self.world = _world(group)
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        spans = [shard_bounds(self.total, r, self.world) for r in range(self.world)]
+        self.sizes = [hi - lo for lo, hi in spans]
+        self.local = self.sizes[self.rank]
+        self.cap = max(self.sizes) if self.sizes else 0
+        row_shape = tuple(row_shape)
+        self.wire = torch.zeros((self.cap,) + row_shape, dtype=dtype, device=device)
+        self.recv = torch.empty((self.world * self.cap,) + row_shape, dtype=dtype, device=device)
+        self.out = torch.empty((self.total,) + row_shape, dtype=dtype, device=device)
+        if all(s == self.cap for s in self.sizes):
+            self.index = None                      # equal shards: the receive buffer already is the result
+        else:
+            self.index = torch.cat([torch.arange(r * self.cap, r * self.cap + s) for r, s in enumerate(self.sizes)]
+                                   ).to(device)
+
+    def __call__(self, rows):
+        if rows.size(0) != self.local:
+            raise ValueError('this rank owns %d boards, got %d rows' % (self.local, rows.size(0)))
+        if self.world == 1:
+            self.out.copy_(rows)
+            return self.out
+        self.wire[:self.local].copy_(rows)                       # (casts to the wire dtype)
+        dist.all_gather_into_tensor(self.recv, self.wire, group=self.group)
+        if self.index is None:
+            return self.recv
+        torch.index_select(self.recv, 0, self.index, out=self.out)
+        return self.out
+
+
+def all_gather_winners(winners, total=None, group=None):
+    """winners [b_local] int64 of every rank -> [total] int64 on every rank, in rank order.  On the wire the
+    winners travel as int8 (values -1..P-1), 1 byte per track: 1 MB for 2^20 tracks, i.e. latency-bound on NVLink.
+    `total` = number of tracks over all ranks, sharded by `shard_bounds` (default: world x b_local, equal shards).
+    One-off convenience; loops should keep a `ShardGather`."""
+    world = _world(group)
+    if world == 1:
         return winners
-    world = dist.get_world_size(group)
-    n = torch.tensor([winners.numel()], dtype=torch.int64, device=winners.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
-    cap = max(sizes)
-    wire = torch.full((cap,), -1, dtype=torch.int8, device=winners.device)
-    wire[:winners.numel()] = winners.to(torch.int8)
-    out = torch.empty((world * cap,), dtype=torch.int8, device=winners.device)
-    dist.all_gather_into_tensor(out, wire, group=group)
-    parts = [out[r * cap:r * cap + sizes[r]] for r in range(world)]
-    return torch.cat(parts).to(torch.int64)
+    total = world * winners.numel() if total is None else total
+    g = ShardGather(total, (), torch.int8, winners.device, group)
+    return g(winners).to(torch.int64)
 
 
-def all_gather_winner_stats(stats, group=None):
+def all_gather_winner_stats(stats, total=None, group=None):
     """Per-board soft labels [boards_local, P+1] f32 of every rank -> [boards, P+1] in rank order
-    (equal shard sizes are not required)."""
-    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+    (`total` boards sharded by `shard_bounds`; default: equal shards)."""
+    world = _world(group)
+    if world == 1:
         return stats
-    world = dist.get_world_size(group)
-    n = torch.tensor([stats.size(0)], dtype=torch.int64, device=stats.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
-    cap = max(sizes)
-    wire = torch.zeros((cap, stats.size(1)), dtype=stats.dtype, device=stats.device)
-    wire[:stats.size(0)] = stats
-    out = torch.empty((world * cap, stats.size(1)), dtype=stats.dtype, device=stats.device)
-    dist.all_gather_into_tensor(out, wire, group=group)
-    return torch.cat([out[r * cap:r * cap + sizes[r]] for r in range(world)])
+    total = world * stats.size(0) if total is None else total
+    g = ShardGather(total, stats.shape[1:], stats.dtype, stats.device, group)
+    return g(stats).clone()
 
 
 def finish_rate(finishes, group=None):

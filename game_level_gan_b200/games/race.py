@@ -226,7 +226,12 @@ class Race(MultiEnvironment):
             if tuple(actions.shape) != (P, B):
                 raise ValueError('actions must have shape [num_players, num_boards] = [%d, %d]' % (P, B))
             stream = torch.cuda.current_stream(dev)
-            anybody_alive = self._any_alive(stream)        # state after the previous step
+            # The reference asks `alive.sum().item() == 0` on every step (a device synchronisation).  Here the answer
+            # is only known if the caller asked `finished()` since the last step - which every loop of the reference's
+            # scripts does (train-gan.py:91: `while ... not game.finished()`); otherwise the step is enqueued
+            # without blocking.  With nobody alive the kernel changes no state either and returns the same rewards; only
+            # the width of the returned zeros (19, games/race.py:353-356) is then not reproduced.
+            anybody_alive = self._alive_known is not False
             self.steps += 1
             if not anybody_alive:                          # games/race.py:353-356 (19-wide quirk)
                 states = torch.zeros((P, B, O + 1), dtype=torch.float32, device=dev)
@@ -234,13 +239,8 @@ class Race(MultiEnvironment):
                 return states, rewards.t()
             states = torch.empty((P, B, O + 2), dtype=torch.float32, device=dev)
             rewards = torch.empty((P, B), dtype=torch.float32, device=dev)
-            hist = None
-            if self._hist is not None and 0 <= self.record_id < B:
-                if self.steps >= self._hist.size(0):
-                    grown = torch.zeros((2 * self._hist.size(0), P, 6), dtype=torch.float32, device=dev)
-                    grown[:self._hist.size(0)] = self._hist
-                    self._hist = grown
-                hist = self._hist
+            hist = self._history_ring(self.steps)
+            if hist is not None:
                 self._hist_steps.append(self.steps)
             self._seq += 1
             c = self._step_const                           # pointers that do not change between resets
@@ -268,30 +268,34 @@ class Race(MultiEnvironment):
         from .rollout import HostStepper
         return HostStepper(self)
 
-    def rollout(self, actions, keep_all=False, chained=True):
+    ROLLOUT_MODES = {'fused': _lib.ROLLOUT_FUSED, 'chained': _lib.ROLLOUT_CHAINED, 'stepwise': _lib.ROLLOUT_STEPWISE}
+
+    def rollout(self, actions, keep_all=False, mode='fused', out=None):
         """T steps with pre-computed actions [T,P,B] (no per-step host work).  Returns the outputs of
         the last step, or of all steps ([T,P,B,O+2], [T,P,B]) with keep_all.  Equivalent to T calls of
         `step` as long as somebody is alive throughout (the 19-wide early-out is not applied).
-        `chained`: consecutive step kernels depend on each other car by car instead of grid by grid, so
-        they overlap (include/glg_b200.h, glg_race_rollout); the results are the same."""
-        dev = self.device
-        with torch.no_grad():
-            actions = actions.detach().to(device=dev, dtype=torch.int64).contiguous()
-            T = actions.size(0)
-            B, P, O = self.num_tracks, self.num_players, self.observation_size
-            shape_s = (T, P, B, O + 2) if keep_all else (P, B, O + 2)
-            shape_r = (T, P, B) if keep_all else (P, B)
-            states = torch.empty(shape_s, dtype=torch.float32, device=dev)
-            rewards = torch.empty(shape_r, dtype=torch.float32, device=dev)
-            check(_lib.lib().glg_race_rollout(
-                self._params, ptr(self._geom), B, self._geom.size(2), ptr(actions), T, ptr(self._valid_tracks),
-                ptr(self._extent), self._state, self.steps + 1, ptr(states), ptr(rewards), int(keep_all), ptr(self._stamp),
-                self._seq + 1, ptr(self._chain) if chained else None,
-                self._variant_code(), _lib.stream_ptr(dev)), 'glg_race_rollout')
-            self._seq += T
-            self.steps += T
-            self._alive_known = None
-            return states, rewards
+        `mode`: 'fused' = one persistent kernel for all T steps (track records stay in shared memory, car state in
+        registers); 'chained' = one kernel per step, consecutive steps depending on each other car by car;
+        'stepwise' = one kernel per step in plain stream order (include/glg_b200.h, glg_race_rollout).  Same results.
+        `out=(states, rewards)`: preallocated output tensors of the shapes above."""
+        return self.rollout_plan(actions, keep_all=keep_all, mode=mode, out=out).run()
+
+    def rollout_plan(self, actions, keep_all=False, mode='fused', out=None):
+        """A `RolloutPlan` for this episode: everything `rollout` prepares (argument checks, output buffers,
+        marshalled pointers), done once; `plan.run()` then only enqueues the kernel(s).  For callers that replay
+        rollouts of one shape many times (benchmarks, action-tape replay)."""
+        return RolloutPlan(self, actions, keep_all, mode, out)
+
+    def _history_ring(self, last_step):
+        """The device-side history ring, grown to hold row `last_step` (None when nothing is recorded)."""
+        if self._hist is None or not (0 <= self.record_id < self.num_tracks):
+            return None
+        if last_step >= self._hist.size(0):
+            grown = torch.zeros((max(2 * self._hist.size(0), last_step + 1), self.num_players, 6), dtype=torch.float32,
+                                device=self.device)
+            grown[:self._hist.size(0)] = self._hist
+            self._hist = grown
+        return self._hist
 
     def snapshot(self):
         """Copy of the mutable episode state (the reference has no env checkpoint; used to rewind
@@ -400,3 +404,55 @@ class Race(MultiEnvironment):
         rows = self._hist[torch.tensor(self._hist_steps, device=self._hist.device)].cpu()
         return [(r[:, 0:2].tolist(), r[:, 2:4].tolist(), [int(a) for a in r[:, 4].tolist()],
                  [bool(a) for a in r[:, 5].tolist()]) for r in rows]
+
+
+class RolloutPlan(object):
+    """Pre-marshalled `glg_race_rollout` call (see `Race.rollout_plan`).  Bound to one episode (one `reset`)."""
+
+    def __init__(self, env, actions, keep_all, mode, out):
+        dev = env.device
+        if mode not in Race.ROLLOUT_MODES:
+            raise ValueError('rollout mode must be one of %s' % sorted(Race.ROLLOUT_MODES))
+        self.env, self.epoch = env, env._epoch
+        self.actions = actions.detach().to(device=dev, dtype=torch.int64).contiguous()
+        B, P, O = env.num_tracks, env.num_players, env.observation_size
+        if self.actions.dim() != 3 or tuple(self.actions.shape[1:]) != (P, B):
+            raise ValueError('actions must have shape [T, num_players, num_boards] = [T, %d, %d]' % (P, B))
+        self.T = T = self.actions.size(0)
+        self.keep_all, self.mode = bool(keep_all), mode
+        shape_s = (T, P, B, O + 2) if keep_all else (P, B, O + 2)
+        shape_r = (T, P, B) if keep_all else (P, B)
+        if out is None:
+            out = (torch.empty(shape_s, dtype=torch.float32, device=dev), torch.empty(shape_r, dtype=torch.float32, device=dev))
+        self.states, self.rewards = out
+        for t, shape in ((self.states, shape_s), (self.rewards, shape_r)):
+            if tuple(t.shape) != shape or t.dtype != torch.float32 or t.device != dev or not t.is_contiguous():
+                raise ValueError('out must be contiguous float32 tensors of shapes %s, %s on %s' % (shape_s, shape_r, dev))
+        self._fn = _lib.lib().glg_race_rollout
+        self._head = (env._params, ptr(env._geom), B, env._geom.size(2), ptr(self.actions), T, ptr(env._valid_tracks),
+                      ptr(env._extent), env._state)
+        self._out = (ptr(self.states), ptr(self.rewards), int(self.keep_all), ptr(env._stamp))
+        self._chain = ptr(env._chain) if mode == 'chained' else None
+        self._tail = (Race.ROLLOUT_MODES[mode], env._variant_code())
+        # kernels one call launches (bench.py reports it): the fused mode needs the production kernel's preconditions
+        fused = mode == 'fused' and env.variant == 'fast' and O == 18 and env._geom.size(2) <= 256 and env._geom.size(2) % 2 == 0
+        self.launches = 1 if fused else T
+
+    def run(self):
+        env = self.env
+        if env._epoch != self.epoch:
+            raise GlgError('the environment was reset after this RolloutPlan was created - make a new one')
+        T = self.T
+        if T == 0:
+            return self.states, self.rewards
+        hist = env._history_ring(env.steps + T)
+        rc = self._fn(*self._head, env.steps + 1, *self._out, env._seq + 1, self._chain, ptr(hist), env.record_id,
+                      *self._tail, torch.cuda.current_stream(env.device).cuda_stream)
+        if rc != 0:
+            check(rc, 'glg_race_rollout')
+        if hist is not None:
+            env._hist_steps.extend(range(env.steps + 1, env.steps + T + 1))
+        env._seq += T
+        env.steps += T
+        env._alive_known = None
+        return self.states, self.rewards

@@ -151,23 +151,36 @@ int glg_race_step(const glg_race_params* params, const float* geom, int32_t B, i
                   int32_t* alive_stamp, int32_t launch_seq, const int32_t* base, float* history,
                   int32_t record_id, int32_t variant, glg_stream_t stream);
 
-/* T consecutive steps with pre-computed actions [T,P,B] (random-action rollouts, replay).
- * Launches T step kernels back to back on `stream`; states_out/rewards_out hold the LAST step's
- * outputs, or all steps if `keep_all` (then [T,P,B,W] / [T,P,B]).  first_step_no as in glg_race_step;
- * launch t uses launch_seq = first_launch_seq + t.
- *   chain  scratch of glg_race_chain_bytes(B, P) bytes (16-byte aligned, zero-filled once) or NULL.  With it, launches 1..T-1 do not wait for the whole previous grid but,
- *          warp by warp, for the previous step of their own car (chain[car] == launch_seq - 1, published with
- *          release/acquire), so consecutive steps overlap; results are identical.  With keep_all the stamp is
- *          published right after the car state is written back (before the ray cast), without it after the
- *          outputs (the steps share one output buffer).  The production kernel with keep_all goes one step
- *          further: the car state travels from launch to launch in six self-validating 64-bit words
- *          {launch number : value} of `chain` (no fences, no second round trip) and only the last launch
- *          writes the state arrays.  The numbers
- *          first_launch_seq .. first_launch_seq+T-1 must be larger than anything stored in `chain` before. */
+/* T consecutive steps with pre-computed actions [T,P,B] (random-action rollouts, replay): the loop of
+ * train-gan.py:86-93 without a policy in it.  states_out/rewards_out hold the LAST step's outputs, or all steps if
+ * `keep_all` (then [T,P,B,W] / [T,P,B]); every step's observation is computed either way.  first_step_no as in
+ * glg_race_step; step t uses launch_seq = first_launch_seq + t.  history / record_id as in glg_race_step (row
+ * first_step_no + t).
+ *   mode   GLG_ROLLOUT_FUSED    ONE persistent launch plays all T steps: a warp keeps its track record in shared
+ *                               memory and its cars' state in registers; per step only the action is read and the
+ *                               observation and reward are written.  Configurations GLG_STEP_PACKED covers (18 rays,
+ *                               N <= 256 even); others fall back to CHAINED (if `chain`) or STEPWISE.
+ *          GLG_ROLLOUT_STEPWISE T step kernels back to back in plain stream order.
+ *          GLG_ROLLOUT_CHAINED  T step kernels; launches 1..T-1 do not wait for the whole previous grid but, warp by
+ *                               warp, for the previous step of their own car (chain[car] == launch_seq - 1, published
+ *                               with release/acquire), so consecutive steps overlap.  With keep_all the stamp is
+ *                               published right after the car state is written back (before the ray cast), without it
+ *                               after the outputs (the steps share one output buffer); the production kernel with
+ *                               keep_all hands the car state from launch to launch in six self-validating 64-bit words
+ *                               {launch number : value} of `chain` (no fences, no second round trip) and only the
+ *                               last launch writes the state arrays.
+ *   chain  scratch of glg_race_chain_bytes(B, P) bytes (16-byte aligned, zero-filled once), required by CHAINED,
+ *          else may be NULL.  The numbers first_launch_seq .. first_launch_seq+T-1 must be larger than anything
+ *          stored in `chain` before.
+ * All modes give identical results.                                                              */
+#define GLG_ROLLOUT_STEPWISE 0
+#define GLG_ROLLOUT_CHAINED  1
+#define GLG_ROLLOUT_FUSED    2
 int glg_race_rollout(const glg_race_params* params, const float* geom, int32_t B, int32_t N,
                      const int64_t* actions, int32_t T, const uint8_t* valid, const float* extent,
                      glg_race_state state, int32_t first_step_no, float* states_out, float* rewards_out, int32_t keep_all,
                      int32_t* alive_stamp, int32_t first_launch_seq, int32_t* chain,
+                     float* history, int32_t record_id, int32_t mode,
                      int32_t variant, glg_stream_t stream);
 
 int64_t glg_race_chain_bytes(int32_t B, int32_t P);

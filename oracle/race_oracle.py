@@ -15,7 +15,7 @@ Why torch and not numpy: the reference's results depend on the exact rounding of
 kernels (``cumsum`` accumulates in double, ``norm`` is sqrt(fma(y,y,x*x)), ``sin``/``cos`` are
 SLEEF) - using the same primitive ops is the only way to be bit-identical to it.
 
-Everything is written per *car* with masks (no ``nonzero`` compaction as the reference does);
+Collisions and sensors are evaluated for the cars the reference selects (``update_mask`` / ``alive_mask``);
 every arithmetic expression that influences a rounding keeps the reference's operation order.
 All line citations are relative to /root/reference/.
 """
@@ -267,10 +267,17 @@ class RaceOracle(object):
         upd = self.alive & moving & valid                  # :380
         rewards = torch.zeros((B, P))
         rewards[~self.finishes] = STEP_PENALTY             # :382-383
-        # collisions (:390, 406-407, 431-432), evaluated for every car and masked by upd
+        # collisions (:385-432): like the reference, only for the cars selected by `upd` (update_mask, :380)
         paths = torch.cat((self.pos, npos), dim=-1)        # [B,P,4]
-        dead = segments_cross(self.walls, paths).any(dim=1) & upd
-        done = segments_cross(self.finish, paths).any(dim=1) & upd
+        dead = torch.zeros((B * P,), dtype=torch.bool)
+        done = torch.zeros((B * P,), dtype=torch.bool)
+        sel_u = upd.view(-1).nonzero().squeeze(-1)
+        if sel_u.numel() > 0:                              # :385
+            car_track = sel_u // P
+            pth = paths.view(-1, 1, 4)[sel_u]              # :390
+            dead[sel_u] = segments_cross(self.walls[car_track], pth).any(dim=1).squeeze(-1)     # :406-407
+            done[sel_u] = segments_cross(self.finish[car_track], pth).any(dim=1).squeeze(-1)    # :431-432
+        dead, done = dead.view(B, P), done.view(B, P)
         self.last_dead, self.last_done, self.last_idx = dead, done, idx
         rewards = torch.where(upd, rewards + (done.float() - dead.float()), rewards)   # :434
         self.alive = self.alive & ~dead & ~done            # :414,435

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '2',
-                          '--warmup', '1'], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          '--warmup', '1', '--cpu-tracks', '256'], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
     assert len(lines) == 1
@@ -26,5 +26,5 @@ def test_reference_arm_prints_the_contract_line():
 def test_reference_arm_other_ranks_stay_silent():
     env = dict(os.environ, RANK='1', WORLD_SIZE='2')
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2',
-                          '--steps', '2', '--warmup', '1'], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+                          '--steps', '2', '--warmup', '1', '--cpu-tracks', '256'], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ''

@@ -29,13 +29,21 @@ def _worker(rank, world, port, q):
         assert torch.equal(local.view(trials, hi - lo, 16, 2), tracks.view(trials, boards, 16, 2)[:, lo:hi])
         w_local = winners_all.view(trials, boards)[:, lo:hi].reshape(-1)
         stats_local = torch.nn.functional.one_hot(w_local + 1, P + 1).view(trials, -1, P + 1).float().mean(0)
-        stats = gdist.all_gather_winner_stats(stats_local)
+        stats = gdist.all_gather_winner_stats(stats_local, total=boards)
         ref = torch.nn.functional.one_hot(winners_all + 1, P + 1).view(trials, -1, P + 1).float().mean(0)
         assert torch.equal(stats, ref)
         # plain winners with unequal shards
         lo2, hi2 = gdist.shard_bounds(winners_all.numel(), rank, world)
-        got = gdist.all_gather_winners(winners_all[lo2:hi2].clone())
+        got = gdist.all_gather_winners(winners_all[lo2:hi2].clone(), total=winners_all.numel())
         assert torch.equal(got, winners_all)
+        # the reusable gatherer: unequal shards (21 rows over 2 ranks), buffers allocated once, called twice
+        sg = gdist.ShardGather(boards, (P + 1,), torch.float32, torch.device('cpu'))
+        assert sg.sizes == [4, 3] and sg.local == hi - lo
+        for rep in range(2):
+            assert torch.equal(sg(stats_local + rep), ref + rep)
+        eq_sg = gdist.ShardGather(8, (), torch.int8, torch.device('cpu'))     # equal shards: no index pass
+        assert eq_sg.index is None
+        assert torch.equal(eq_sg(torch.arange(4, dtype=torch.int64) + 4 * rank).long(), torch.arange(8))
         fin = (winners_all[lo2:hi2] >= 0)
         assert abs(gdist.finish_rate(fin) - float((winners_all >= 0).float().mean())) < 1e-6
         q.put((rank, 'ok'))

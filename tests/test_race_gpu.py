@@ -159,10 +159,10 @@ def test_rollout_equals_steps_and_winner_stats():
     a = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
     a.reset(tracks)
     per_step = [a.step(acts[s].cuda()) for s in range(T)]
-    for chained in (True, False):
+    for mode in ('fused', 'chained', 'stepwise'):
         b = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
         b.reset(tracks)
-        states, rewards = b.rollout(acts.cuda(), keep_all=True, chained=chained)
+        states, rewards = b.rollout(acts.cuda(), keep_all=True, mode=mode)
         assert eq(states, torch.stack([s for s, _ in per_step])) and eq(rewards, torch.stack([r for _, r in per_step]))
         assert eq(a.positions, b.positions) and eq(a.scores, b.scores) and a.steps == b.steps
         assert a.finished() == b.finished()
@@ -170,10 +170,10 @@ def test_rollout_equals_steps_and_winner_stats():
         c = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
         c.reset(tracks)
         snap = c.snapshot()
-        c.rollout(acts[:17].cuda(), chained=chained)
+        c.rollout(acts[:17].cuda(), mode=mode)
         c.restore(snap)
-        c.rollout(acts[:30].cuda(), chained=chained)
-        s_last, r_last = c.rollout(acts[30:].cuda(), chained=chained)
+        c.rollout(acts[:30].cuda(), mode=mode)
+        s_last, r_last = c.rollout(acts[30:].cuda(), mode=mode)
         assert eq(s_last, per_step[-1][0]) and eq(r_last, per_step[-1][1]) and eq(c.positions, a.positions)
         assert c.finished() == a.finished()
     w = a.winners()
@@ -231,8 +231,8 @@ def test_reset_from_generator_levels():
 
 @pytest.mark.parametrize('P', [1, 3, 4, 8])
 def test_chained_rollout_other_player_counts(P):
-    """Chained rollouts (LL hand-over with keep_all, release/acquire stamps without) for 1, 3 and 4 cars per
-    track - an idle half warp, two warps per track - against per-step calls."""
+    """Fused (one persistent kernel) and chained rollouts (LL hand-over with keep_all, release/acquire stamps
+    without) for 1, 3, 4 and 8 cars per track - an idle half warp, several warps per track - against per-step calls."""
     from game_level_gan_b200.games import Race, RaceCar
     cars = [RaceCar(*c) for c in [(60., 4., 40.), (60., 1., 80.), (80., 2., 60.), (50., 3., 50.), (70., 2., 30.),
                                   (40., 4., 90.), (90., 1., 45.), (55., 2., 70.)][:P]]
@@ -245,10 +245,10 @@ def test_chained_rollout_other_player_counts(P):
     a = Race(timeout=40., cars=cars, framerate=1. / 20., log_history=False)
     a.reset(tracks)
     per_step = [a.step(acts[s].cuda()) for s in range(T)]
-    for keep_all in (True, False):
+    for keep_all, mode in ((True, 'fused'), (False, 'fused'), (True, 'chained'), (False, 'chained'), (True, 'stepwise')):
         b = Race(timeout=40., cars=cars, framerate=1. / 20., log_history=False)
         b.reset(tracks)
-        states, rewards = b.rollout(acts.cuda(), keep_all=keep_all)
+        states, rewards = b.rollout(acts.cuda(), keep_all=keep_all, mode=mode)
         if keep_all:
             assert eq(states, torch.stack([s for s, _ in per_step])) and eq(rewards, torch.stack([r for _, r in per_step]))
         else:
