@@ -108,11 +108,20 @@ def record_tape(env, tracks, seed, device):
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+    """Samples SM clock and throttle reasons through NVML; `summary()` uses the samples taken between `mark_start()`
+    and `mark_end()` (the timed region).  Started before the warm-up so that NVML is initialised by then."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        self.index, self.stop_flag, self.samples, self.max_mhz = index, False, [], None
+        self.t0 = self.t1 = None
+        self.error = None
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def run(self):
         try:
@@ -123,22 +132,32 @@ class ClockSampler(threading.Thread):
             names = {getattr(nv, n): n for n in dir(nv) if n.startswith('nvmlClocksEventReason') or
                      n.startswith('nvmlClocksThrottleReason')}
             while not self.stop_flag:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                 try:
                     mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
                     mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                reasons = set()
                 for bit, n in names.items():
                     if isinstance(bit, int) and bit and (mask & bit) == bit and 'None' not in n and 'All' not in n:
-                        self.reasons.add(n.replace('nvmlClocksEventReason', '').replace('nvmlClocksThrottleReason', ''))
-                time.sleep(0.002)
+                        reasons.add(n.replace('nvmlClocksEventReason', '').replace('nvmlClocksThrottleReason', ''))
+                self.samples.append((time.perf_counter(), mhz, reasons))
+                time.sleep(0.001)
         except Exception as e:  # noqa: BLE001
-            self.reasons.add('nvml_unavailable:%s' % type(e).__name__)
+            self.error = 'nvml_unavailable:%s' % type(e).__name__
 
     def summary(self):
-        s = sorted(self.samples)
-        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz,
-                'reasons': sorted(r for r in self.reasons if r not in ('GpuIdle', 'ApplicationsClocksSetting'))}
+        inside = [x for x in self.samples if self.t0 is not None and self.t0 <= x[0] <= (self.t1 or x[0])]
+        if not inside and self.samples and self.t0 is not None:       # region shorter than the sampling period
+            inside = [min(self.samples, key=lambda x: abs(x[0] - self.t0))]
+        s = sorted(x[1] for x in inside)
+        reasons = set()
+        for x in inside:
+            reasons |= x[2]
+        if self.error:
+            reasons.add(self.error)
+        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz, 'samples': len(s),
+                'reasons': sorted(r for r in reasons if r not in ('GpuIdle', 'ApplicationsClocksSetting'))}
 
 
 def measured_peak():
@@ -350,8 +369,8 @@ def parity_gate(rep, device, tracks_n=256, steps=40):
 
 def run_config4(args, rank, world, device, barrier, total_tracks, trials=4, T=200):
     """Config 4 of BASELINE.json: 2^20 iid-9 tracks x 4 cars sharded over the ranks by board (all `trials` repetitions
-    of a board on one rank, train-gan.py:84), tracks and forward-biased random actions generated ON DEVICE per rank
-    (seed + rank), one fused rollout of T = 200 steps, then the per-board winner statistics
+    of a board on one rank, train-gan.py:84), tracks and actions generated ON DEVICE per rank
+    (seed + rank; the actions are a tape of the heuristic driver recorded once, untimed), one fused rollout of T = 200 steps, then the per-board winner statistics
     (train-gan.py:103-104) all-gathered - rollout, statistics and collective inside the timed region."""
     import torch.distributed as dist
     from game_level_gan_b200 import dist as gdist
@@ -367,14 +386,19 @@ def run_config4(args, rank, world, device, barrier, total_tracks, trials=4, T=20
     env = Race(timeout=40., cars=[RaceCar(*c) for c in CONFIG4_CARS], framerate=1. / 20., log_history=False, device=device,
                variant=args.variant)
     t0 = time.perf_counter()
-    env.reset_levels(levels)
+    states, _ = env.reset_levels(levels)
     torch.cuda.synchronize()
     reset_s = time.perf_counter() - t0
+    # action tape: the heuristic driver plays the episode once, closed loop, on the device (untimed); the timed region
+    # replays the tape from the reset state.  (iid random actions would kill every car within ~100 steps, and dead
+    # cars skip the ray cast.)
     snap = env.snapshot()
-    acts = torch.randint(0, 9, (T, P, B), generator=gen, device=device)
-    fwd = torch.rand((T, P, B), generator=gen, device=device) < 0.6
-    acts[fwd] = 1
-    del fwd
+    acts = torch.empty((T, P, B), dtype=torch.int64, device=device)
+    for t in range(T):
+        acts[t] = driver_actions(states, gen)
+        states = env.step(acts[t])[0]
+    alive_tape_end = float(env.alive.float().mean())
+    del states
     plan = env.rollout_plan(acts, keep_all=False, mode=args.rollout_mode)
     gather = gdist.ShardGather(boards, (P + 1,), torch.float32, device)
     times = []
@@ -401,7 +425,8 @@ def run_config4(args, rank, world, device, barrier, total_tracks, trials=4, T=20
            'stats_rows': int(stats.size(0)), 'stats_sum': float(stats.sum()),
            'gathered_bytes': int(stats.numel() * 4), 'launches': plan.launches + 2 + (1 if world > 1 else 0),
            'roofline_frac': (ALGO_BYTES_PER_TRACK + ALGO_BYTES_PER_CAR * P) * B * T / (ms * 1e-3) / (measured_peak()[0] * 1e9),
-           'note': 'forward-biased random actions: cars die (dead cars skip the ray cast), see alive_fraction_end'}
+           'alive_fraction_tape_end': alive_tape_end,
+           'actions': 'tape of the heuristic driver (closed loop, recorded untimed on the device), replayed from the reset state'}
     del plan, acts, env
     torch.cuda.empty_cache()
     return out
@@ -502,14 +527,15 @@ def run_b200(args, rank, world):
         return e0.elapsed_time(e1)
 
     # warm-up: the identical block (same call shapes, same buffers), at least --warmup steps and every batch once
+    sampler = ClockSampler(local)
+    sampler.start()
     n_warm = max(R, -(-max(args.warmup, 3) // max(K, 1)))
     for i in range(n_warm):
         timed_block(i)
     repeats = args.repeats if args.repeats > 0 else max(3, min(15, 6000 // max(K, 1)))
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.05)
+    sampler.mark_start()
     times = [timed_block(i) for i in range(repeats)]
+    sampler.mark_end()
     sampler.stop_flag = True
     tm = torch.tensor(times, device=device, dtype=torch.float64)
     if world > 1:

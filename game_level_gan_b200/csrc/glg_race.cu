@@ -470,28 +470,36 @@ static void launch_fused_rollout(const glg_race_params* pr, const float* geom, i
     const int P = pr->num_players;
     const int WPT = (P + 1) / 2;
     const int TPB = P <= 2 ? 2 : 1;
-    FusedArgs a{geom, actions, valid, extent, st, states_out, rewards_out, alive_stamp, history,
-                B, N, T, first_step_no, history ? record_id : -1, first_launch_seq + T - 1, keep_all ? 1 : 0,
-                0, 0, 0, 0, 0, 0};
-    fused_layout(a, N, 2 * WPT);
+    FusedArgs a{};
+    a.geom = geom; a.actions = actions; a.valid = valid; a.extent = extent; a.st = st;
+    a.states_out = states_out; a.rewards_out = rewards_out; a.alive_stamp = alive_stamp; a.history = history;
+    a.B = B; a.N = N; a.T = T; a.first_step_no = first_step_no; a.record_id = history ? record_id : -1;
+    a.last_seq = first_launch_seq + T - 1; a.keep_all = keep_all ? 1 : 0;
+    a.lay = fused_layout(N, 2 * WPT);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((B + TPB - 1) / TPB);
     cfg.blockDim = dim3(32 * WPT * TPB);
-    cfg.dynamicSmemBytes = (size_t)TPB * a.track_bytes;
+    cfg.dynamicSmemBytes = (size_t)TPB * a.lay.track_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    static size_t smem_opted[2] = {48 * 1024, 48 * 1024};
-    if (cfg.dynamicSmemBytes > smem_opted[TPB - 1]) {
-        if (TPB == 2) cudaFuncSetAttribute(race_rollout_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
-        else cudaFuncSetAttribute(race_rollout_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
-        smem_opted[TPB - 1] = cfg.dynamicSmemBytes;
+    // instantiations: the reference's own track length (N = 130) with 2 / 4 car slots, and the generic ones
+    using kernel_t = void (*)(const glg_race_params, const FusedArgs);
+    kernel_t kernel;
+    int slot;
+    if (TPB == 2 && N == 130) { kernel = race_rollout_fused_kernel<2, 130, 2>; slot = 0; }
+    else if (TPB == 2) { kernel = race_rollout_fused_kernel<2, 0, 0>; slot = 1; }
+    else if (N == 130 && WPT == 2) { kernel = race_rollout_fused_kernel<1, 130, 4>; slot = 2; }
+    else { kernel = race_rollout_fused_kernel<1, 0, 0>; slot = 3; }
+    static size_t smem_opted[4] = {48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024};
+    if (cfg.dynamicSmemBytes > smem_opted[slot]) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+        smem_opted[slot] = cfg.dynamicSmemBytes;
     }
-    if (TPB == 2) cudaLaunchKernelEx(&cfg, race_rollout_fused_kernel<2>, *pr, a);
-    else cudaLaunchKernelEx(&cfg, race_rollout_fused_kernel<1>, *pr, a);
+    cudaLaunchKernelEx(&cfg, kernel, *pr, a);
 }
 
 }  // namespace glg

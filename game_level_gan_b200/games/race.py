@@ -317,8 +317,11 @@ class Race(MultiEnvironment):
         return self._alive_known
 
     def finished(self):
-        """games/race.py:502-504."""
-        return self.steps > self.steps_limit or not self._any_alive()
+        """games/race.py:502-504.  Always refreshes the host's view of "anybody alive" (one 4 KB read + a stream
+        synchronisation, what the reference's `alive.sum().item()` costs), which the next `step` uses for the
+        reference's early-out."""
+        anybody_alive = self._any_alive()
+        return self.steps > self.steps_limit or not anybody_alive
 
     def winners(self):
         """games/race.py:506-529 -> int64 [B] in {-1, 0..P-1}."""

@@ -192,3 +192,33 @@ def test_sharded_winner_stats_equal_the_unsharded_ones():
         assert parts[-1].shape == (hi - lo, P + 1)
     assert eq(torch.cat(parts), ref)
     assert float(ref[:, 1:].sum()) > 0                                  # some boards do have winners
+
+
+@pytest.mark.parametrize('L,P', [(64, 2), (200, 2), (254, 3), (30, 4), (10, 2)])
+def test_fused_rollout_other_track_lengths(L, P):
+    """Track lengths other than the reference's 128 segments take the generic instantiations of the fused kernel
+    (run-time shared-memory layout and trip counts; L = 10 is shorter than the arg-min window): against per-step calls
+    of the literal kernel."""
+    from game_level_gan_b200.games import Race, RaceCar
+    cars = [RaceCar(*c) for c in [(60., 4., 40.), (60., 1., 80.), (80., 2., 60.), (50., 3., 50.)][:P]]
+    g = torch.Generator().manual_seed(500 + L)
+    B, T = 77, 40
+    tracks = torch.zeros(B, L, 2)
+    tracks[:, :, 0] = torch.linspace(-1., 1., 9)[torch.randint(0, 9, (B, L), generator=g)]
+    tracks[B // 2:, :, 1] = torch.rand((B - B // 2, L), generator=g)
+    acts = torch.randint(0, 9, (T, P, B), generator=g)
+    acts = torch.where(torch.rand((T, P, B), generator=g) < 0.6, torch.ones_like(acts), acts)
+    a = Race(timeout=40., cars=cars, framerate=1. / 20., log_history=False, variant='brute')
+    b = Race(timeout=40., cars=cars, framerate=1. / 20., log_history=False, variant='fast')
+    sa0, _ = a.reset(tracks)
+    sb0, _ = b.reset(tracks)
+    assert eq(sa0, sb0)
+    ref = [a.step(acts[s].cuda()) for s in range(T)]
+    plan = b.rollout_plan(acts.cuda(), keep_all=True, mode='fused')
+    assert plan.launches == 1
+    st, rw = plan.run()
+    assert eq(st, torch.stack([s for s, _ in ref])) and eq(rw, torch.stack([r for _, r in ref]))
+    for x, y in ((a.positions, b.positions), (a.directions, b.directions), (a.speeds, b.speeds), (a.alive, b.alive),
+                 (a.finishes, b.finishes), (a.scores, b.scores)):
+        assert eq(x, y)
+    assert eq(a.winners(), b.winners())

@@ -363,6 +363,8 @@ def test_degenerate_car_on_the_wall_line():
     ref = envs['brute']
     saw_nan = False
     for s, a in enumerate([noop, noop, fwd, fwd, noop, fwd]):
+        for env in envs.values():
+            env.finished()                 # like the reference's loop (train-gan.py:91); arms the 19-wide early-out
         so, ro_ = ref.step(a.cuda())
         co, cr = orc.step(a.numpy())
         assert eq(so, co) and eq(ro_, cr), ('oracle', s)

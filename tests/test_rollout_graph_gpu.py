@@ -108,6 +108,7 @@ def test_host_stepper_matches_step():
     hd = d.host_stepper()
     right = torch.full((2, 4), 4, dtype=torch.int64)          # forward-right until the wall
     for s in range(400):
+        c.finished()                       # `step` itself never blocks: the early-out needs the loop's own question
         sc, rc = c.step(right.cuda())
         sd, rd = hd.step(right)
         assert sc.shape == sd.shape and eq(sc, sd) and eq(rc, rd), 'step %d' % s

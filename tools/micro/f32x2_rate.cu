@@ -44,6 +44,10 @@ __global__ void __launch_bounds__(256) body(float* out, int iters, float m, floa
                 x[i].y = __fadd_rn(__fmul_rn(x[i].y, m), a);
             }
         }
+        if (MODE & 4) {     // 12 integer instructions: neither the fp32 pipes nor the integer pipe saturate - issue decides
+#pragma unroll
+            for (int i = 0; i < 4; ++i) u[i] = (u[i] ^ (u[(i + 1) & 3] + it)) + (u[i] >> 3);
+        }
         if (MODE & 2) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
@@ -91,6 +95,8 @@ int main()
     run<1>("packed fp only", out, iters, 16, 0);
     run<2>("scalar fp + int", out, iters, 32, 48);
     run<3>("packed fp + int", out, iters, 16, 48);
+    run<4>("scalar fp + few int", out, iters, 32, 12);
+    run<5>("packed fp + few int", out, iters, 16, 12);
     printf("(clock = nominal max; ratios between the lines are what matters)\n");
     return 0;
 }
