@@ -159,26 +159,25 @@ __global__ void game_update_kernel(const float2* __restrict__ left, const float2
     const int seg0 = pseg[pl];
     int next = seg0;
     bool alive = true, done = false;
-    if (seg0 < 0) {
-        // the reference would index left[-1] here (undefined); a car that backed out of the track stays dead
-        alive = false;
-    } else {
-        while (next < length) {                                  // :220-238 forward walk
+    // `next_seg` is an int and `track.length` a size_t (game_helpers.cpp:105, 215): both comparisons of the forward
+    // part are UNSIGNED in the reference.  A car that backed out over the start line (cell -1, reported dead then)
+    // therefore skips the forward walk and is reported `finished` (and not dead) by every later call, its cell
+    // staying at -1 - reproduced here, pinned by tests/golden/game_update.npz (case C).
+    while ((unsigned)next < (unsigned)length) {                  // :220-238 forward walk
+        const P2 la = ld2(L + next), lb = ld2(L + next + 1), ra = ld2(R + next), rb = ld2(R + next + 1);
+        if (segments_cross(la, lb, pos, np) || segments_cross(ra, rb, pos, np)) { alive = false; break; }
+        if (turn(lb, rb, np) > 0) break;                         // stayed in this cell
+        ++next;
+    }
+    if (alive && (unsigned)next >= (unsigned)length) done = true;    // :240-243
+    if (next == seg0 && alive && !done) {                        // :245-269 backward walk
+        while (next >= 0) {
             const P2 la = ld2(L + next), lb = ld2(L + next + 1), ra = ld2(R + next), rb = ld2(R + next + 1);
             if (segments_cross(la, lb, pos, np) || segments_cross(ra, rb, pos, np)) { alive = false; break; }
-            if (turn(lb, rb, np) > 0) break;                     // stayed in this cell
-            ++next;
+            if (turn(la, ra, np) < 0) break;
+            --next;
         }
-        if (alive && next >= length) done = true;                // :240-243
-        if (next == seg0 && alive && !done) {                    // :245-269 backward walk
-            while (next >= 0) {
-                const P2 la = ld2(L + next), lb = ld2(L + next + 1), ra = ld2(R + next), rb = ld2(R + next + 1);
-                if (segments_cross(la, lb, pos, np) || segments_cross(ra, rb, pos, np)) { alive = false; break; }
-                if (turn(la, ra, np) < 0) break;
-                --next;
-            }
-            if (next < 0) alive = false;
-        }
+        if (next < 0) alive = false;
     }
     ppos[pl] = make_float2(np.x, np.y);                          // :271-272
     pseg[pl] = next;

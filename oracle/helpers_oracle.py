@@ -1,7 +1,9 @@
 """Pure-Python oracle for the `game_helpers` entry points (TEST INFRASTRUCTURE - checker only).
 
 Game.update_players is Boost-free in the reference and is restated literally (game_helpers.cpp:191-279,
-with orientation / on_segment / segment_intersect of :22-66) in numpy float32 arithmetic.
+with orientation / on_segment / segment_intersect of :22-66) in numpy float32 arithmetic - PINNED against
+tests/golden/game_update.npz, which the reference's own C++ produced (oracle/build_ref.py compiles those line
+ranges of /root/reference/games/game_helpers.cpp where they lie; tests/golden/make_golden_helpers.py drives it).
 The Boost.Geometry-backed functions (collision, smallest_distance, is_valid, Game.validate_tracks,
 Game.smallest_distance) have no golden vectors upstream and Boost is not available here:
 PARITY UNPINNED for those - they are defined as in csrc/glg_helpers.cu and checked here against the
@@ -58,28 +60,27 @@ class GameOracle(object):
             old = self.pos[pl].copy()
             nxt = int(self.seg[pl])
             alive, done = True, False
-            if nxt < 0:
-                alive = False          # the reference reads out of bounds here; defined as "stays dead"
-            else:
-                while nxt < length:
+            # `next_seg` is an int, `track.length` a size_t: the two comparisons of the forward part are unsigned in the
+            # reference (game_helpers.cpp:105, 215, 220, 240) - a car at cell -1 skips the walk and is "finished"
+            while 0 <= nxt < length:
+                if segment_intersect(L[nxt], L[nxt + 1], old, new) or segment_intersect(R[nxt], R[nxt + 1], old, new):
+                    alive = False
+                    break
+                if orientation(L[nxt + 1], R[nxt + 1], new) > 0:
+                    break
+                nxt += 1
+            if alive and (nxt >= length or nxt < 0):
+                done = True
+            if nxt == self.seg[pl] and alive and not done:
+                while nxt >= 0:
                     if segment_intersect(L[nxt], L[nxt + 1], old, new) or segment_intersect(R[nxt], R[nxt + 1], old, new):
                         alive = False
                         break
-                    if orientation(L[nxt + 1], R[nxt + 1], new) > 0:
+                    if orientation(L[nxt], R[nxt], new) < 0:
                         break
-                    nxt += 1
-                if alive and nxt >= length:
-                    done = True
-                if nxt == self.seg[pl] and alive and not done:
-                    while nxt >= 0:
-                        if segment_intersect(L[nxt], L[nxt + 1], old, new) or segment_intersect(R[nxt], R[nxt + 1], old, new):
-                            alive = False
-                            break
-                        if orientation(L[nxt], R[nxt], new) < 0:
-                            break
-                        nxt -= 1
-                    if nxt < 0:
-                        alive = False
+                    nxt -= 1
+                if nxt < 0:
+                    alive = False
             self.pos[pl] = new
             self.seg[pl] = nxt
             dead.append(0 if alive else 1)

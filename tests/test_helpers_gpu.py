@@ -1,7 +1,9 @@
 """`game_helpers` facade (free functions + Game) on the GPU against the known-answer case of the
-reference's run_game_helpers.py, the literal Python restatement of Game.update_players, and float64
+reference's run_game_helpers.py, golden vectors of Game.update_players produced by the reference's own C++
+(tests/golden/game_update.npz), the literal Python restatement of it, and float64
 restatements of the Boost-backed semantics (parity unpinned upstream, see oracle/helpers_oracle.py)."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -60,6 +62,31 @@ def test_game_update_players_matches_literal_restatement():
         seen_dead += int(od.sum())
         seen_fin += int(of.sum())
     assert seen_fin > 0
+
+
+@pytest.mark.parametrize('case', ['A', 'B', 'C'])
+def test_game_update_players_matches_reference_cpp(case):
+    """glg_game_update_players against flags the REFERENCE's C++ produced (game_helpers.cpp:191-279 compiled by
+    oracle/build_ref.py): A = the agents' positions, every car; B = the reference's own call pattern (alive cars only,
+    rows (old, new) of stride 4, games/race.py:394); C = random jumps incl. cars behind the start line (cell -1:
+    the unsigned comparison quirk)."""
+    from game_level_gan_b200.games import game_helpers as gh
+    from tests.helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, 'game_update.npz'))
+    src = 'C' if case == 'C' else 'A'
+    left, right, P = t(z[src + '_left']).cuda(), t(z[src + '_right']).cuda(), int(z[src + '_P'])
+    game = gh.Game(left, right, P)
+    rows, dead, fin = z[case + '_rows'], z[case + '_dead'], z[case + '_fin']
+    K = rows.shape[1]
+    for s in range(rows.shape[0]):
+        idx = z['B_idx'][s][z['B_idx'][s] >= 0] if case == 'B' else np.arange(K)
+        n = len(idx)
+        if n == 0:
+            continue
+        d, f = game.update_players(t(idx.astype(np.int64)).cuda(), t(rows[s][:n]).cuda())
+        assert eq(d, dead[s][:n]) and eq(f, fin[s][:n]), 'case %s step %d' % (case, s)
+    assert case == 'B' or fin.sum() > 0
+    assert case != 'C' or dead.sum() > 0
 
 
 def test_stateless_helpers_against_float64_definitions():
