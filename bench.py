@@ -611,12 +611,38 @@ def run_b200(args, rank, world):
     e2e_loop(e2e_steps)
     t1.record()
     barrier()
+    loop_ms = t0.elapsed_time(t1)
+    if world > 1:
+        tmx = torch.tensor([loop_ms], device=device)
+        dist.all_reduce(tmx, op=dist.ReduceOp.MAX)
+        loop_ms = float(tmx.item())
+    closed_loop_value = world * e2e_steps * B_TRACKS * P_CARS / (loop_ms * 1e-3)
+
+    # the same bytes per step through `Race.host_rollout` (action tape and observations in pinned host memory, chunks
+    # of steps pipelined over copy-in / compute / copy-out streams, ONE host synchronisation per call of CYCLE steps)
+    hr = env.host_rollout(CYCLE, chunk=args.e2e_chunk, mode=args.rollout_mode)
+    tape_h = host_acts[PREROLL:PREROLL + CYCLE]
+    n_calls_e2e = max(2, e2e_steps // CYCLE)
+
+    def e2e_rollouts(k):
+        for i in range(k):
+            env.restore(snap)
+            st, rw = hr.run(tape_h)                                    # host tape in, host observations + rewards out
+            sink[0] += rw[-1, 0, 0] + st[-1, 0, 0, 0]                  # the host reads the results
+
+    e2e_rollouts(2)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    e2e_rollouts(n_calls_e2e)
+    t1.record()
+    barrier()
     e2e_ms = t0.elapsed_time(t1)
     if world > 1:
         tmx = torch.tensor([e2e_ms], device=device)
         dist.all_reduce(tmx, op=dist.ReduceOp.MAX)
         e2e_ms = float(tmx.item())
-    e2e_value = world * e2e_steps * B_TRACKS * P_CARS / (e2e_ms * 1e-3)
+    e2e_value = world * n_calls_e2e * CYCLE * B_TRACKS * P_CARS / (e2e_ms * 1e-3)
 
     extra = {}
     if not args.no_extra:
@@ -662,10 +688,18 @@ def run_b200(args, rank, world):
                      'algorithmic_bytes_per_launch': algo_step * chunks[0] if fused else algo_step,
                      'steps_per_launch': chunks[0] if fused else 1,
                      'launch_ms': ms / n_calls if fused else step_ms},
-        'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'steps': e2e_steps,
-                'api': 'Race.host_stepper().step(host actions) -> host observations, rewards (one CUDA graph per step)',
-                'h2d_bytes_per_step': P_CARS * B_TRACKS * 8 + 16,
-                'd2h_bytes_per_step': P_CARS * B_TRACKS * (O_RAYS + 2 + 1) * 4 + 4096},
+        'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'steps': n_calls_e2e * CYCLE,
+                'api': 'Race.host_rollout(%d steps, chunk=%d).run(host action tape) -> host observations, rewards of every step '
+                       '(pinned memory; chunks pipelined over copy-in / compute / copy-out streams, one host '
+                       'synchronisation per call; open loop)' % (CYCLE, args.e2e_chunk),
+                'h2d_bytes_per_step': hr.h2d_bytes // CYCLE, 'd2h_bytes_per_step': hr.d2h_bytes // CYCLE,
+                'ms_per_step': e2e_ms / (n_calls_e2e * CYCLE),
+                'closed_loop': {'value': closed_loop_value, 'unit': 'env-steps/s', 'steps': e2e_steps,
+                                'api': 'Race.host_stepper().step(host actions) -> host observations, rewards: one CUDA graph '
+                                       '(H2D, step kernel, D2H) and one synchronisation PER STEP, what a host-resident '
+                                       'policy in the loop pays',
+                                'h2d_bytes_per_step': P_CARS * B_TRACKS * 8 + 16,
+                                'd2h_bytes_per_step': P_CARS * B_TRACKS * (O_RAYS + 2 + 1) * 4 + 4096}},
         'gpu_launches': launches[0], 'clocks': sampler.summary(), 'parity': parity, 'extra': extra,
     }
     if value < e2e_value:
@@ -762,6 +796,7 @@ def main():
     ap.add_argument('--repeats', type=int, default=0, help='timed blocks (0 = 3..15 depending on --steps); the median is reported')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-extra', action='store_true', help='skip the config 3 / 4 / 5 records')
+    ap.add_argument('--e2e-chunk', type=int, default=10, help='steps per pipelined chunk of the end-to-end host rollout')
     ap.add_argument('--replicas', type=int, default=REPLICAS, help='independent config-2 batches the calls of a block rotate over')
     ap.add_argument('--tracks', type=int, default=4096, help='tracks per batch (default = config 2)')
     ap.add_argument('--cpu-tracks', type=int, default=None, help='tracks of the CPU arm (default: all, = same config)')

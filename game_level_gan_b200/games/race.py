@@ -268,6 +268,12 @@ class Race(MultiEnvironment):
         from .rollout import HostStepper
         return HostStepper(self)
 
+    def host_rollout(self, T, chunk=25, mode='fused'):
+        """A `HostRollout` (games/rollout.py) for this episode: T-step rollouts whose action tape and observations
+        live in pinned host memory, chunked and pipelined over copy-in / compute / copy-out streams."""
+        from .rollout import HostRollout
+        return HostRollout(self, T, chunk, mode)
+
     ROLLOUT_MODES = {'fused': _lib.ROLLOUT_FUSED, 'chained': _lib.ROLLOUT_CHAINED, 'stepwise': _lib.ROLLOUT_STEPWISE}
 
     def rollout(self, actions, keep_all=False, mode='fused', out=None):
@@ -407,6 +413,28 @@ class Race(MultiEnvironment):
         rows = self._hist[torch.tensor(self._hist_steps, device=self._hist.device)].cpu()
         return [(r[:, 0:2].tolist(), r[:, 2:4].tolist(), [int(a) for a in r[:, 4].tolist()],
                  [bool(a) for a in r[:, 5].tolist()]) for r in rows]
+
+    # ---- drawing (games/race.py:531-820).  The rasterisation is OpenCV's, as in the reference; the
+    # data path (track records, history ring, batched ray lengths of the recorded cars) is race_render.py ----
+    def record_episode(self, filename):
+        """games/race.py:531-646: `filename`.mp4 of the recorded board (needs `log_history`)."""
+        from . import race_render
+        return race_render.record_episode(self, filename)
+
+    def tracks_images(self, top_n=3):
+        """games/race.py:648-689 -> uint8 [top_n, 256, 256, 3]."""
+        from . import race_render
+        return race_render.tracks_images(self, top_n)
+
+    def prettier_tracks(self, top_n=3, size=1024, pad=0.05):
+        """games/race.py:691-749 -> uint8 RGBA [top_n, size, size, 4]."""
+        from . import race_render
+        return race_render.prettier_tracks(self, top_n, size, pad)
+
+    def prettier_tracks_svg(self, top_n=3, size=1024, pad=0.05):
+        """games/race.py:751-820 -> [svgwrite.Drawing] (needs the `svgwrite` package, like the reference)."""
+        from . import race_render
+        return race_render.prettier_tracks_svg(self, top_n, size, pad)
 
 
 class RolloutPlan(object):

@@ -159,3 +159,75 @@ class HostStepper(object):
         env._seq += 1
         env._alive_known = bool((self._stamp_np == env._seq).any())
         return self.states_h, self.rewards_h
+
+
+class HostRollout(object):
+    """`Race.rollout` for callers whose action tape and observation buffers live on the HOST (pinned memory): T steps in
+    chunks of `chunk` steps, pipelined over three streams -
+
+        copy-in  : H2D of chunk c+1's actions
+        compute  : the fused rollout kernel of chunk c (one launch per chunk, glg_race_rollout)
+        copy-out : D2H of chunk c-1's observations and rewards
+
+    so that the PCIe transfers of neighbouring chunks hide behind the kernel and behind each other (H2D and D2H use the
+    two DMA directions).  Every step's actions cross the bus host -> device and every step's observations and rewards
+    come back - the same bytes as T calls of `HostStepper.step` - but the host only synchronises once per call.
+    Open loop by construction (the tape is given up front); closed-loop host policies use `HostStepper`.
+    Results are those of `Race.rollout(actions, keep_all=True)`; bound to one episode like `RolloutPlan`.
+    """
+
+    def __init__(self, env, T, chunk=25, mode='fused'):
+        if env.num_tracks is None or env.num_tracks == 0:
+            raise GlgError('HostRollout needs a reset environment with at least one track')
+        if T <= 0 or chunk <= 0:
+            raise ValueError('T and chunk must be positive')
+        self.env, self.epoch, self.T = env, env._epoch, int(T)
+        dev = env.device
+        B, P, O = env.num_tracks, env.num_players, env.observation_size
+        self.actions_h = torch.zeros((T, P, B), dtype=torch.int64).pin_memory()
+        self.states_h = torch.zeros((T, P, B, O + 2), dtype=torch.float32).pin_memory()
+        self.rewards_h = torch.zeros((T, P, B), dtype=torch.float32).pin_memory()
+        self.actions_d = torch.zeros((T, P, B), dtype=torch.int64, device=dev)
+        self.states_d = torch.empty((T, P, B, O + 2), dtype=torch.float32, device=dev)
+        self.rewards_d = torch.empty((T, P, B), dtype=torch.float32, device=dev)
+        self.bounds = [(lo, min(lo + chunk, T)) for lo in range(0, T, chunk)]
+        self.plans = [env.rollout_plan(self.actions_d[lo:hi], keep_all=True, mode=mode,
+                                       out=(self.states_d[lo:hi], self.rewards_d[lo:hi])) for lo, hi in self.bounds]
+        self.launches = sum(p.launches for p in self.plans)
+        self.s_in, self.s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self.ev_in = [torch.cuda.Event() for _ in self.bounds]
+        self.ev_done = [torch.cuda.Event() for _ in self.bounds]
+        self.h2d_bytes = self.actions_h.numel() * 8
+        self.d2h_bytes = (self.states_h.numel() + self.rewards_h.numel()) * 4
+
+    def run(self, actions=None):
+        """actions: [T,P,B] integer CPU tensor / numpy array (copied into the pinned staging buffer), or None when the
+        caller filled `self.actions_h` itself.  -> (states [T,P,B,O+2], rewards [T,P,B]): pinned host tensors, complete
+        when the call returns, overwritten by the next call."""
+        env = self.env
+        if env._epoch != self.epoch:
+            raise GlgError('the environment was reset after this HostRollout was created - make a new one')
+        if actions is not None:
+            a = actions.numpy() if torch.is_tensor(actions) else np.asarray(actions)
+            if tuple(a.shape) != tuple(self.actions_h.shape):
+                raise ValueError('actions must have shape [T, num_players, num_boards] = %s' % (tuple(self.actions_h.shape),))
+            np.copyto(self.actions_h.numpy(), a, casting='unsafe')
+        main = torch.cuda.current_stream(env.device)
+        self.s_in.wait_stream(main)                        # the staging buffers may still be read by the previous call
+        self.s_out.wait_stream(main)
+        with torch.no_grad():
+            for c, (lo, hi) in enumerate(self.bounds):
+                with torch.cuda.stream(self.s_in):
+                    self.actions_d[lo:hi].copy_(self.actions_h[lo:hi], non_blocking=True)
+                    self.ev_in[c].record(self.s_in)
+            for c, (lo, hi) in enumerate(self.bounds):
+                main.wait_event(self.ev_in[c])
+                self.plans[c].run()                        # on the caller's stream: ordered after its reset / restore
+                self.ev_done[c].record(main)
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(self.ev_done[c])
+                    self.states_h[lo:hi].copy_(self.states_d[lo:hi], non_blocking=True)
+                    self.rewards_h[lo:hi].copy_(self.rewards_d[lo:hi], non_blocking=True)
+        main.wait_stream(self.s_out)
+        main.synchronize()
+        return self.states_h, self.rewards_h

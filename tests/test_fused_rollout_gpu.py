@@ -222,3 +222,37 @@ def test_fused_rollout_other_track_lengths(L, P):
                  (a.finishes, b.finishes), (a.scores, b.scores)):
         assert eq(x, y)
     assert eq(a.winners(), b.winners())
+
+
+@pytest.mark.parametrize('T,chunk', [(40, 25), (37, 5), (12, 40)])
+def test_host_rollout_equals_device_rollout(T, chunk):
+    """`Race.host_rollout`: pinned host action tape in, pinned host observations / rewards out, chunks pipelined over
+    copy-in / compute / copy-out streams - same results as `Race.rollout(keep_all=True)` and as per-step calls of the
+    literal kernel, twice in a row (the staging buffers are reused) and after a rewind."""
+    from game_level_gan_b200.games import Race, RaceConfig
+    tracks, g = _iid9(300, 91)
+    acts = torch.randint(0, 9, (T, 2, 300), generator=g)
+    acts = torch.where(torch.rand((T, 2, 300), generator=g) < 0.6, torch.ones_like(acts), acts)
+    a = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False, variant='brute')
+    b = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
+    a.reset(tracks)
+    b.reset(tracks)
+    ref = [a.step(acts[s].cuda()) for s in range(T)]
+    ref_s, ref_r = torch.stack([s for s, _ in ref]), torch.stack([r for _, r in ref])
+    snap = b.snapshot()
+    hr = b.host_rollout(T, chunk=chunk)
+    assert hr.launches == len(hr.bounds) == -(-T // chunk)
+    assert hr.h2d_bytes == T * 2 * 300 * 8 and hr.d2h_bytes == T * 2 * 300 * 21 * 4
+    for rep in range(2):
+        st, rw = hr.run(acts if rep == 0 else acts.numpy())
+        assert not st.is_cuda and st.is_pinned() and st.shape == (T, 2, 300, 20)
+        assert eq(st, ref_s) and eq(rw, ref_r), rep
+        assert b.steps == T + 1 and eq(b.positions, a.positions) and eq(b.alive, a.alive) and eq(b.scores, a.scores)
+        st.zero_()
+        rw.zero_()
+        b.restore(snap)
+    with pytest.raises(ValueError):
+        hr.run(acts[:-1])
+    b.reset(tracks)
+    with pytest.raises(Exception):
+        hr.run(acts)
