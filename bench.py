@@ -796,7 +796,7 @@ def main():
     ap.add_argument('--repeats', type=int, default=0, help='timed blocks (0 = 3..15 depending on --steps); the median is reported')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-extra', action='store_true', help='skip the config 3 / 4 / 5 records')
-    ap.add_argument('--e2e-chunk', type=int, default=10, help='steps per pipelined chunk of the end-to-end host rollout')
+    ap.add_argument('--e2e-chunk', type=int, default=25, help='steps per pipelined chunk of the end-to-end host rollout')
     ap.add_argument('--replicas', type=int, default=REPLICAS, help='independent config-2 batches the calls of a block rotate over')
     ap.add_argument('--tracks', type=int, default=4096, help='tracks per batch (default = config 2)')
     ap.add_argument('--cpu-tracks', type=int, default=None, help='tracks of the CPU arm (default: all, = same config)')
