@@ -252,15 +252,17 @@ class Race(MultiEnvironment):
             self._alive_known = None
             return states, rewards
 
-    def step_into(self, actions, states_out, rewards_out, base, offset, stamp=None):
+    def step_into(self, actions, states_out, rewards_out, base, offset, stamp=None, history=None):
         """Capture-safe step for CUDA graphs (games/rollout.py): no allocation, no host synchronisation, no
         early-out; the step number and launch number are `offset` plus the two int32 counters in the
-        device tensor `base`; steps beyond base[2] do nothing (include/glg_b200.h)."""
+        device tensor `base`; steps beyond base[2] do nothing (include/glg_b200.h).  `history`: the device-side
+        history ring (`_history_ring(last step)`, grown by the caller BEFORE capture - its address is baked in)."""
         B = self.num_tracks
         check(_lib.lib().glg_race_step(
             self._params, ptr(self._geom), B, self._geom.size(2), ptr(actions), ptr(self._valid_tracks),
             ptr(self._extent), self._state, offset, ptr(states_out), ptr(rewards_out),
-            ptr(self._stamp if stamp is None else stamp), offset, ptr(base), None, -1, self._variant_code(), _lib.stream_ptr(self.device)), 'glg_race_step')
+            ptr(self._stamp if stamp is None else stamp), offset, ptr(base), ptr(history),
+            self.record_id if history is not None else -1, self._variant_code(), _lib.stream_ptr(self.device)), 'glg_race_step')
 
     def host_stepper(self):
         """A `HostStepper` (games/rollout.py) for this episode: `step` with host-resident actions / observations

@@ -32,12 +32,14 @@ class GraphedRollout(object):
         self.rewards = torch.zeros((P, B), dtype=torch.float32, device=dev)
         self.actions = torch.zeros((P, B), dtype=torch.int64, device=dev)
         self.base = torch.zeros((3,), dtype=torch.int32, device=dev)      # {step number, launch number} so far, last step
+        # history of the recorded board (games/race.py:492-494): rows up to the last step a replay can execute
+        self.hist = env._history_ring(env.steps_limit + 1 + self.k)
         self.graph = None
 
     def _body(self):
         for j in range(1, self.k + 1):
             self.actions.copy_(self.act(self.states))
-            self.env.step_into(self.actions, self.states, self.rewards, self.base, j)
+            self.env.step_into(self.actions, self.states, self.rewards, self.base, j, history=self.hist)
         self.base[:2] += self.k
 
     def capture(self):
@@ -61,7 +63,9 @@ class GraphedRollout(object):
 
     def run(self, states, max_replays=None):
         """Play the episode from the observation `states` (of `reset` or the last `step`) to its end.
-        Returns (last states, last rewards)."""
+        Returns (states, rewards) of the LAST REPLAYED step - up to k-1 steps after the one that ended the episode
+        (dead and finished cars are frozen there: zero readings, the -0.01 / 0 step rewards), not the terminating
+        step's own +1 / -1 rewards; callers that need per-step outputs use `Race.rollout(keep_all=True)` or `step`."""
         env = self.env
         if env._epoch != self.epoch:
             raise GlgError('the environment was reset after this GraphedRollout was created: the graph is bound to '
@@ -80,6 +84,7 @@ class GraphedRollout(object):
             env.steps += self.k
             env._seq += self.k
             env._alive_known = None
+        ran = replays * self.k
         if replays and env.finished():
             # the reference's loop stops right after the step that ended the episode
             env._stamp_host.copy_(env._stamp)
@@ -87,8 +92,14 @@ class GraphedRollout(object):
             last_alive = int(env._stamp_host.max())                # launch number after which somebody was still alive
             by_death = (max(last_alive, start_seq) - start_seq) + 1 if last_alive >= start_seq else 0
             by_time = env.steps_limit + 1 - start_steps
-            ran = replays * self.k
             env.steps = start_steps + min(ran, by_death, by_time)
+            # launches past the time limit were no-ops and left no stamp: the launch counter goes back to the last one
+            # that executed, so that "anybody alive" (stamp == launch counter) keeps meaning what it says
+            executed = max(0, min(ran, by_time))
+            env._seq = start_seq + executed
+            env._alive_known = bool((env._stamp_np == env._seq).any()) if executed else None
+        if self.hist is not None and env.steps > start_steps:
+            env._hist_steps.extend(range(start_steps + 1, env.steps + 1))
         return self.states, self.rewards
 
 
@@ -127,12 +138,13 @@ class HostStepper(object):
         states_d = self.out_d[:n_obs].view(P, B, O + 2)
         rewards_d = self.out_d[n_obs:n_obs + n_rw].view(P, B)
         stamp_d = self.out_d[n_obs + n_rw:].view(torch.int32)            # private stamp (launch numbers only grow)
+        self.hist = env._history_ring(env.steps_limit + 2)              # recorded board, games/race.py:492-494
         self.stream = torch.cuda.Stream(device=dev)
         self.graph = torch.cuda.CUDAGraph()
         self.stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.no_grad(), torch.cuda.graph(self.graph, stream=self.stream):
             self.in_d.copy_(self.in_h, non_blocking=True)
-            env.step_into(actions_d, states_d, rewards_d, base_d, 1, stamp=stamp_d)
+            env.step_into(actions_d, states_d, rewards_d, base_d, 1, stamp=stamp_d, history=self.hist)
             self.out_h.copy_(self.out_d, non_blocking=True)
 
     def step(self, actions):
@@ -158,6 +170,8 @@ class HostStepper(object):
         env.steps += 1
         env._seq += 1
         env._alive_known = bool((self._stamp_np == env._seq).any())
+        if self.hist is not None and env.steps < self.hist.size(0):
+            env._hist_steps.append(env.steps)
         return self.states_h, self.rewards_h
 
 
