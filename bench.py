@@ -486,6 +486,8 @@ def run_b200(args, rank, world):
     local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
+    from game_level_gan_b200 import dist as gdist
+    numa_cores = gdist.bind_host_to_gpu(local) if world > 1 else None      # before any pinned allocation
     if world > 1:
         with stdout_to_stderr():
             dist.init_process_group('nccl', device_id=device)
@@ -681,7 +683,8 @@ def run_b200(args, rank, world):
                    'collective': None if world == 1 else
                        'all-gather of the winners (int8) at every episode end, i.e. after every full %d-step call '
                        '(%d in a block of %d steps); a lone one takes %.1f us' % (CYCLE, K // CYCLE, K, collective_us),
-                   'parallelism': 'dp%d (tracks sharded)' % world},
+                   'parallelism': 'dp%d (tracks sharded)' % world,
+                   'host_cores_rank0': sorted(numa_cores) if numa_cores else 'unchanged'},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': traffic.get('dram_bytes_per_launch'), 'traffic_note': traffic.get('note'), 'peak_source': peak_kind,
                      'algorithmic_bytes_per_step': algo_step,

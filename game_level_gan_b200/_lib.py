@@ -7,7 +7,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'csrc', 'libglg_b200.so')
+LIB_PATH = os.environ.get('GLG_LIB_PATH') or os.path.join(HERE, 'csrc', 'libglg_b200.so')    # (override: A/B builds, tools/ab.py)
 
 MAX_PLAYERS = 8
 MAX_RAYS = 32

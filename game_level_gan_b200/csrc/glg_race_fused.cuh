@@ -93,12 +93,28 @@ __device__ __forceinline__ float2 sub2(float2 a, float2 b) {
 __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 __device__ __forceinline__ float sqrt_fast(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// ray_setup (glg_sensors.cuh) with the table entry already in registers
+__device__ __forceinline__ void ray_setup_cs(float rc, float rs, P2 s, P2 nd, P2& d, P2& f) {
+    d = P2{xadd(xmul(nd.x, rc), xmul(nd.y, rs)), xadd(xmul(nd.x, -rs), xmul(nd.y, rc))};
+    f = P2{xadd(s.x, xmul(1000.f, d.x)), xadd(s.y, xmul(1000.f, d.y))};
+}
+
 // wall w of the polyline in the reference's orientation, from the structure-of-arrays copy (see wall_by_line_index)
 __device__ __forceinline__ void wall_soa(const float* xs, const float* ys, int N, int w, P2& p, P2& q) {
     const float x0 = xs[w], x1 = xs[w + 1], y0 = ys[w], y1 = ys[w + 1];
     const bool rev = w < N;
     p = rev ? P2{x1, y1} : P2{x0, y0};
     q = rev ? P2{x0, y0} : P2{x1, y1};
+}
+
+// one evaluated (wall, ray) pair into the car's per-ray minima: +inf (no hit, the common case) changes nothing and is
+// not sent; NaN is recorded in the mask (torch.min propagates it)
+__device__ __forceinline__ void fused_report(PackedCar* car, int i, float tw) {
+    if (tw != tw) atomicOr(&car->nan_mask, 1u << i);
+    else if (tw < INF) atomicMin(&car->tmin[i], __float_as_int(tw));
 }
 
 // brute-force sensors of one car by its 16 lanes (rare: a precondition of the pruning failed), SoA polyline
@@ -154,6 +170,12 @@ __device__ __noinline__ bool fused_collide_all(const float* xs, const float* ys,
 #ifndef GLG_FUSED_MINBLOCKS1
 #define GLG_FUSED_MINBLOCKS1 8
 #endif
+#ifndef GLG_F_ACT_SMEM
+#define GLG_F_ACT_SMEM 1          // actions fetched 16 steps at a time by cp.async (0: one __ldg per step, a step ahead)
+#endif
+#ifndef GLG_F_RAYTAB
+#define GLG_F_RAYTAB 1            // ray table in shared memory (0: per-lane indexed loads from the parameter bank)
+#endif
 constexpr int FW = 16;                         // centre points in the arg-min window (one per lane of a group)
 constexpr int FW_BACK = 5;                     // of which behind the last arg-min (cars mostly advance)
 
@@ -179,6 +201,14 @@ race_rollout_fused_kernel(const __grid_constant__ glg_race_params pr, const Fuse
     const bool track_on = b < B;
     const bool car_on = track_on && p < P;
     const int ci = wt * 2 + grp;
+
+    // per-warp copy of the ray table (cos, sin of the 18 ray angles): per-lane indexed loads from the parameter
+    // (constant) bank serialise, shared memory does not; and the cars' actions, fetched 16 steps at a time by
+    // asynchronous copies (one step per lane) one block ahead - no register holds a prefetched value across a step
+    __shared__ float2 s_raytab[4][PK_RAYS];
+    __shared__ long long s_acts[8][2][PK_G];
+    if (lane < PK_RAYS) s_raytab[warp][lane] = make_float2(pr.ray_cos[lane], pr.ray_sin[lane]);
+    long long (*acts)[PK_G] = s_acts[threadIdx.x >> 4];
 
     unsigned char* tbase = smem_raw + (unsigned)tslot * lay.track_bytes;
     const float2* centre = reinterpret_cast<const float2*>(tbase + lay.centre_off);
@@ -222,8 +252,13 @@ race_rollout_fused_kernel(const __grid_constant__ glg_race_params pr, const Fuse
         spd = a.st.speeds[k];
         ok = a.valid[b] != 0;
         ext = __ldg(reinterpret_cast<const float2*>(a.extent) + b);
+#if GLG_F_ACT_SMEM
+        if (gl < a.T) cp_async_8(&acts[0][gl], a.actions + goff + (size_t)gl * PB);          // steps 0..15
+#else
         act_next = (int)__ldg(a.actions + goff);
+#endif
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     const int pc = min(p, GLG_MAX_PLAYERS - 1);
     const float vmax = pr.vmax[pc];
     const float Lmax = ext.y;
@@ -258,8 +293,20 @@ race_rollout_fused_kernel(const __grid_constant__ glg_race_params pr, const Fuse
 
     for (int t = 0; t < a.T; ++t) {
         const int step_no = a.first_step_no + t;
+#if !GLG_F_ACT_SMEM
         int act = act_next;
         if (car_on && t + 1 < a.T) act_next = (int)__ldg(a.actions + goff + PB);
+#else
+        if ((t & (PK_G - 1)) == 0) {
+            // the block of 16 actions this step starts was requested 16 steps ago; request the next one
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            const int tn = t + PK_G + gl;
+            if (car_on && tn < a.T) cp_async_8(&acts[((t >> 4) + 1) & 1][gl], a.actions + goff + (size_t)(PK_G + gl) * PB);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        int act = car_on ? (int)acts[(t >> 4) & 1][t & (PK_G - 1)] : 0;
+#endif
         // ---- kinematics (uniform within a group) ----
         act = min(max(act, 0), 8);
         if (!alive || !ok) act = 0;                                           // race.py:359
@@ -354,11 +401,21 @@ race_rollout_fused_kernel(const __grid_constant__ glg_race_params pr, const Fuse
         if (gl < 2) car->tmin[PK_RAYS + gl] = 0;
         {
             P2 d, f;
-            ray_setup(pr, gl, np, nd, d, f);
+#if GLG_F_RAYTAB
+            const float2 cs = s_raytab[warp][gl];
+#else
+            const float2 cs = make_float2(pr.ray_cos[gl], pr.ray_sin[gl]);
+#endif
+            ray_setup_cs(cs.x, cs.y, np, nd, d, f);
             car->ray[gl] = make_float4(d.x, d.y, f.x, f.y);
             car->tmin[gl] = 0x7f800000;
             if (gl < O - PK_G) {
-                ray_setup(pr, PK_G + gl, np, nd, d, f);
+#if GLG_F_RAYTAB
+                const float2 cs1 = s_raytab[warp][PK_G + gl];
+#else
+                const float2 cs1 = make_float2(pr.ray_cos[PK_G + gl], pr.ray_sin[PK_G + gl]);
+#endif
+                ray_setup_cs(cs1.x, cs1.y, np, nd, d, f);
                 car->ray[PK_G + gl] = make_float4(d.x, d.y, f.x, f.y);
                 car->tmin[PK_G + gl] = 0x7f800000;
             }
@@ -474,8 +531,7 @@ race_rollout_fused_kernel(const __grid_constant__ glg_race_params pr, const Fuse
                         mask &= mask - 1;
                         const float4 r = car->ray[i];
                         const float tw = ray_wall_t_fast(pp, qq, np, P2{r.x, r.y}, P2{r.z, r.w});
-                        if (tw != tw) atomicOr(&car->nan_mask, 1u << i);
-                        else atomicMin(&car->tmin[i], __float_as_int(tw));
+                        fused_report(car, i, tw);
                         if (mask) {                                    // further rays of this wall: second round
                             int posn = atomicAdd(&car->qn, __popc(mask));
                             const int wcode = w << 5;
@@ -529,8 +585,7 @@ race_rollout_fused_kernel(const __grid_constant__ glg_race_params pr, const Fuse
                 wall_soa(xs, ys, N, w, pp, qq);
                 const float4 r = car->ray[i];
                 const float tw = ray_wall_t_fast(pp, qq, np, P2{r.x, r.y}, P2{r.z, r.w});
-                if (tw != tw) atomicOr(&car->nan_mask, 1u << i);
-                else atomicMin(&car->tmin[i], __float_as_int(tw));
+                fused_report(car, i, tw);
             }
         }
         const bool brute_s = alive && (!safe || overflow);

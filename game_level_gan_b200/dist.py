@@ -102,3 +102,26 @@ def finish_rate(finishes, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(s, group=group)
     return (s[0] / s[1].clamp(min=1.)).item()
+
+
+def bind_host_to_gpu(device_index):
+    """One process per GPU: run this rank's host threads on the CPU cores NVML reports as local to its GPU (same NUMA
+    node / PCIe root), so that the pinned staging buffers it allocates afterwards (first touch) and its copy threads
+    sit next to the GPU - host<->device copies of eight ranks otherwise funnel through one socket.  Only cores the
+    process is already allowed to use are kept; returns the new affinity set, or None when nothing was changed
+    (NVML missing, no information, or no allowed core is local to the GPU)."""
+    import os
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(int(device_index))
+        words = nv.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+    except Exception:  # noqa: BLE001
+        return None
+    local = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+    allowed = os.sched_getaffinity(0)
+    cores = local & allowed
+    if not cores or cores == allowed:
+        return None
+    os.sched_setaffinity(0, cores)
+    return cores

@@ -73,3 +73,16 @@ def test_gather_world_size_2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert results == {0: 'ok', 1: 'ok'}, results
+
+
+def test_bind_host_to_gpu_is_harmless_without_a_gpu():
+    """No NVML device here: nothing changes and None comes back; on a GPU box the set returned is a subset of the
+    cores the process was allowed to use."""
+    import os
+    from game_level_gan_b200 import dist as gdist
+    before = os.sched_getaffinity(0)
+    got = gdist.bind_host_to_gpu(0)
+    try:
+        assert got is None or (got and got <= before)
+    finally:
+        os.sched_setaffinity(0, before)

@@ -120,3 +120,53 @@ def test_host_stepper_matches_step():
     d.reset(tr)
     with pytest.raises(GlgError):
         hd.step(right)
+
+
+def test_graphed_rollout_history_and_state_after_a_time_limit_end():
+    """An episode that ends by the time limit with cars alive: the graph's replays past the limit are no-ops, the
+    environment afterwards answers like after the reference's loop (somebody IS alive, so a further `step` is a normal
+    20-wide step, games/race.py:353-356), and with `log_history` the recorded board's history equals the loop's."""
+    from game_level_gan_b200.games import GraphedRollout, Race, RaceConfig
+    g = torch.Generator().manual_seed(5)
+    B = 64
+    tracks = torch.zeros(B, 128, 2)
+    tracks[:, :, 0] = torch.linspace(-1., 1., 9)[torch.randint(0, 9, (B, 128), generator=g)] * 0.3
+    with torch.no_grad():
+        env = Race(timeout=2., cars=RaceConfig.cars, framerate=1. / 20., log_history=True)
+        env.record(3)
+        pol = RecurrentArgmaxPolicy(2, B, 20, seed=4)
+        states, any_valid = env.reset(tracks)
+        while any_valid and not env.finished():
+            states, rewards = env.step(pol(states))
+        env2 = Race(timeout=2., cars=RaceConfig.cars, framerate=1. / 20., log_history=True)
+        env2.record(3)
+        pol2 = RecurrentArgmaxPolicy(2, B, 20, seed=4)
+        states2, _ = env2.reset(tracks)
+        GraphedRollout(env2, pol2, steps_per_replay=7, on_reset=pol2.reset).run(states2)
+        assert env.steps == env2.steps == env.steps_limit + 1 and int(env.alive.sum()) > 0
+        assert env2._any_alive() and env._any_alive()
+        h1, h2 = env.history, env2.history
+        assert len(h1) == len(h2) == env.steps and h1 == h2
+        noop = torch.zeros((2, B), dtype=torch.int64, device='cuda')
+        s1, r1 = env.step(noop)
+        s2, r2 = env2.step(noop)
+        assert s1.shape == s2.shape == (2, B, 20) and eq(s1, s2) and eq(r1, r2)
+
+
+def test_host_stepper_records_history():
+    from game_level_gan_b200.games import Race, RaceConfig
+    g = torch.Generator().manual_seed(9)
+    tracks = torch.zeros(8, 128, 2)
+    tracks[:, :, 0] = torch.linspace(-1., 1., 9)[torch.randint(0, 9, (8, 128), generator=g)]
+    acts = torch.randint(0, 9, (30, 2, 8), generator=g)
+    a = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=True)
+    b = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=True)
+    for e in (a, b):
+        e.record(2)
+        e.reset(tracks)
+    hs = b.host_stepper()
+    for s in range(30):
+        a.finished()
+        a.step(acts[s].cuda())
+        hs.step(acts[s])
+    assert len(a.history) == 31 and a.history == b.history
