@@ -5,7 +5,8 @@ from .race import Race, RaceCar
 from .race_utils import RaceConfig, predefined_tracks, race_game
 from .pytorch_wrapper import PytorchWrapper
 from . import game_helpers
-from .rollout import GraphedRollout, HostStepper
+from .rollout import CaptureSafePolicy, GraphedRollout, HostRollout, HostStepper, capture_safe_agents
 
 __all__ = ['MultiEnvironment', 'Pacman', 'Race', 'RaceCar', 'RaceConfig', 'predefined_tracks', 'race_game',
-           'PytorchWrapper', 'game_helpers', 'GraphedRollout', 'HostStepper']
+           'PytorchWrapper', 'game_helpers', 'GraphedRollout', 'HostStepper', 'HostRollout', 'CaptureSafePolicy',
+           'capture_safe_agents']

@@ -103,6 +103,67 @@ class GraphedRollout(object):
         return self.states, self.rewards
 
 
+class CaptureSafePolicy(torch.nn.Module):
+    """Makes a recurrent policy network of the reference (policies/LSTMPolicy.py, ConvLSTMPolicy.py: `state` = list of
+    (h, c) tensors that `forward` REBINDS to fresh tensors on every call) usable inside a captured CUDA graph: the
+    recurrent state lives in fixed buffers, each forward starts from them and copies the new state back in place.
+    Same numbers as the wrapped network; `reset_state`, `state_dict` and `load_state_dict` are the wrapped network's,
+    which is all agents/PPOAgent.py:40-63 touches."""
+
+    def __init__(self, net):
+        super().__init__()
+        self.net = net
+        self._buf = None
+
+    def reset_state(self):
+        if self._buf is None:
+            self.net.reset_state()
+        else:
+            for h, c in self._buf:
+                h.zero_()
+                c.zero_()
+
+    def forward(self, inputs):
+        if self._buf is not None:
+            self.net.state = [(h, c) for h, c in self._buf]
+        out = self.net(inputs)
+        if self._buf is None:                      # first call (eager warm-up): adopt the shapes the network chose
+            self._buf = [(h.clone(), c.clone()) for h, c in self.net.state]
+        else:
+            for (bh, bc), (h, c) in zip(self._buf, self.net.state):
+                bh.copy_(h)
+                bc.copy_(c)
+        self.net.state = None                      # nothing outside the buffers survives the call
+        return out
+
+    def state_dict(self, *args, **kwargs):
+        return self.net.state_dict(*args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        return self.net.load_state_dict(*args, **kwargs)
+
+
+def capture_safe_agents(agents, deterministic=False):
+    """The reference's agents (agents/PPOAgent.py) for `GraphedRollout`: wraps `agent.network` / `agent.old_network` in
+    `CaptureSafePolicy` (in place) and returns (act, on_reset) where act(states [P,B,O+2]) -> actions [P,B] is
+    train-gan.py:92 - `torch.stack([a.act(s, training=False) for a, s in zip(agents, states)])` - and on_reset() is
+    `for a in agents: a.reset()` (train-gan.py:95-96)."""
+    for a in agents:
+        for name in ('network', 'old_network'):
+            net = getattr(a, name, None)
+            if net is not None and not isinstance(net, CaptureSafePolicy):
+                setattr(a, name, CaptureSafePolicy(net))
+
+    def act(states):
+        return torch.stack([a.act(s, deterministic=deterministic, training=False) for a, s in zip(agents, states)], dim=0)
+
+    def on_reset():
+        for a in agents:
+            a.reset()
+
+    return act, on_reset
+
+
 class HostStepper(object):
     """`Race.step` for callers whose policies live on the HOST: actions come from and observations go to
     (pinned) host memory every step.  One CUDA graph holds the whole round trip - H2D of the actions and of the

@@ -170,3 +170,61 @@ def test_host_stepper_records_history():
         a.step(acts[s].cuda())
         hs.step(acts[s])
     assert len(a.history) == 31 and a.history == b.history
+
+
+def _stock_agents(seed, P=2):
+    """The reference's own PPOAgent + LSTMPolicy (agents/PPOAgent.py, policies/LSTMPolicy.py) from baseline/_ref (made by
+    tools/make_baseline_ref.py; travels with the working tree, absent in a bare checkout -> skip)."""
+    import os
+    import sys
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(root, 'agents')):
+        pytest.skip('baseline/_ref/agents not present (python tools/make_baseline_ref.py)')
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from agents import PPOAgent
+    from policies import LSTMPolicy
+    torch.manual_seed(seed)
+    agents = [PPOAgent(9, LSTMPolicy(20, 9)) for _ in range(P)]
+    for a in agents:
+        with torch.no_grad():
+            a.network.policy.bias[1] += 1.0          # bias towards "forward" so that cars travel
+        a.reset()                                    # old_network <- network
+    return agents
+
+
+def test_graphed_rollout_with_the_reference_ppo_agents():
+    """train-gan.py:86-96 with the STOCK agents: the reference's loop (`a.act(s, training=False)` per agent and step,
+    greedy so that both runs are deterministic) against GraphedRollout driving the same agents through
+    `capture_safe_agents` - same final environment, same step count, same winners."""
+    from game_level_gan_b200.games import GraphedRollout, Race, RaceConfig, capture_safe_agents
+    g = torch.Generator().manual_seed(77)
+    B = 128
+    tracks = torch.zeros(B, 128, 2)
+    tracks[:, :, 0] = torch.linspace(-1., 1., 9)[torch.randint(0, 9, (B, 128), generator=g)] * 0.5
+    with torch.no_grad():
+        env = Race(timeout=6., cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
+        agents = _stock_agents(3)
+        states, any_valid = env.reset(tracks)
+        while any_valid and not env.finished():
+            actions = torch.stack([a.act(s, deterministic=True, training=False) for a, s in zip(agents, states)], dim=0)
+            states, rewards = env.step(actions)
+        for a in agents:
+            a.reset()
+        env2 = Race(timeout=6., cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
+        agents2 = _stock_agents(3)
+        act, on_reset = capture_safe_agents(agents2, deterministic=True)
+        states2, _ = env2.reset(tracks)
+        roll = GraphedRollout(env2, act, steps_per_replay=10, on_reset=on_reset)
+        roll.run(states2)
+        assert env.steps == env2.steps and env.steps > 20
+        for a, b in ((env.positions, env2.positions), (env.directions, env2.directions), (env.speeds, env2.speeds),
+                     (env.alive, env2.alive), (env.finishes, env2.finishes), (env.scores, env2.scores)):
+            assert eq(a, b)
+        assert eq(env.winners(), env2.winners())
+        assert float(env.positions[:, :, 1].max()) > 1.0                    # the cars did drive
+        # a second episode with the same graph (agents reset, new states): still the loop's result
+        states2, _ = env2.reset(tracks)
+        roll2 = GraphedRollout(env2, act, steps_per_replay=10, on_reset=on_reset)
+        roll2.run(states2)
+        assert env2.steps == env.steps and eq(env.positions, env2.positions)

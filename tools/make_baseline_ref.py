@@ -2,7 +2,8 @@
 
     python tools/make_baseline_ref.py [/root/reference]
 
-Copies the reference's `games/` and `utils/` packages (the only ones `games/race.py` imports) into baseline/_ref/,
+Copies the reference's `games/` and `utils/` packages (the only ones `games/race.py` imports) and `agents/`, `policies/`
+(the stock PPOAgent / LSTMPolicy that tests/test_rollout_graph_gpu.py drives through GraphedRollout) into baseline/_ref/,
 which is git-ignored (it never enters this repository's history) but travels to the GPU box with the working tree.
 The reference has no setup.py / pyproject, so `pip install --target baseline/_ref /root/reference` fails; this is
 the same outcome by plain copy.  Without baseline/_ref bench.py times the torch-op restatement instead
@@ -24,10 +25,10 @@ def main():
         sys.exit('no reference at %s' % src)
     shutil.rmtree(dst, ignore_errors=True)
     os.makedirs(dst)
-    for pkg in ('games', 'utils'):
+    for pkg in ('games', 'utils', 'agents', 'policies'):      # agents / policies: tests/test_rollout_graph_gpu.py (PPOAgent.act)
         shutil.copytree(os.path.join(src, pkg), os.path.join(dst, pkg),
                         ignore=shutil.ignore_patterns('__pycache__', '*.pyc'))
-    print('copied %s/{games,utils} -> %s' % (src, dst))
+    print('copied %s/{games,utils,agents,policies} -> %s' % (src, dst))
 
 
 if __name__ == '__main__':
