@@ -238,7 +238,11 @@ race_rollout_fused_kernel(const __grid_constant__ glg_race_params pr, const Fuse
     // ---- car state: read once ----
     const int k = b * P + p;
     const size_t PB = (size_t)P * B;
-    size_t goff = (size_t)p * B + b;                                       // element [t][p][b] of the [T,P,B] arrays
+    const size_t goff = (size_t)p * B + b;                                 // element [0][p][b] of the [T,P,B] arrays
+    // output cursors: [t][p][b] with keep_all (advanced by one step's worth per step), else [p][b]
+    float* rw_out = a.rewards_out + goff;
+    float* st_out = a.states_out + goff * (PK_RAYS + 2);
+    const size_t rw_step = a.keep_all ? PB : 0, st_step = rw_step * (PK_RAYS + 2);
     bool alive = false, fin = false, ok = false;
     float2 dir = make_float2(0.f, 1.f), pos = make_float2(0.f, 0.f);
     float spd = 0.f;
@@ -295,14 +299,14 @@ race_rollout_fused_kernel(const __grid_constant__ glg_race_params pr, const Fuse
         const int step_no = a.first_step_no + t;
 #if !GLG_F_ACT_SMEM
         int act = act_next;
-        if (car_on && t + 1 < a.T) act_next = (int)__ldg(a.actions + goff + PB);
+        if (car_on && t + 1 < a.T) act_next = (int)__ldg(a.actions + goff + (size_t)(t + 1) * PB);
 #else
         if ((t & (PK_G - 1)) == 0) {
             // the block of 16 actions this step starts was requested 16 steps ago; request the next one
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();
             const int tn = t + PK_G + gl;
-            if (car_on && tn < a.T) cp_async_8(&acts[((t >> 4) + 1) & 1][gl], a.actions + goff + (size_t)(PK_G + gl) * PB);
+            if (car_on && tn < a.T) cp_async_8(&acts[((t >> 4) + 1) & 1][gl], a.actions + goff + (size_t)tn * PB);
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
         int act = car_on ? (int)acts[(t >> 4) & 1][t & (PK_G - 1)] : 0;
@@ -565,9 +569,8 @@ race_rollout_fused_kernel(const __grid_constant__ glg_race_params pr, const Fuse
         const float drag = xsub(1.f, xmul(xsub(1.f, ft != 0 ? 1.f : 0.f), pr.drag));   // race.py:452
         const float speed = xmul(nv, drag);                                    // race.py:455
         const bool emit = a.keep_all != 0 || t == a.T - 1;
-        const size_t ooff = a.keep_all ? goff : goff - (size_t)t * PB;       // [t][p][b], or [p][b] when only the last step is kept
         if (car_on && gl == 0) {
-            if (emit) a.rewards_out[ooff] = reward;
+            if (emit) *rw_out = reward;
             if (a.history && b == a.record_id) {                               // race.py:492-494
                 float* hrow = a.history + ((size_t)step_no * P + p) * 6;
                 hrow[0] = np.x; hrow[1] = np.y; hrow[2] = nd.x; hrow[3] = nd.y; hrow[4] = (float)act; hrow[5] = alive ? 1.f : 0.f;
@@ -594,7 +597,7 @@ race_rollout_fused_kernel(const __grid_constant__ glg_race_params pr, const Fuse
 
         // ---- observation pack [P,B,O+2] (race.py:496-500) ----
         if (car_on && emit) {
-            float* out = a.states_out + ooff * (O + 2);
+            float* out = st_out;
             const unsigned nanm = car->nan_mask;
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
@@ -619,7 +622,8 @@ race_rollout_fused_kernel(const __grid_constant__ glg_race_params pr, const Fuse
         dir = make_float2(nd.x, nd.y);
         pos = make_float2(np.x, np.y);
         spd = speed;
-        goff += PB;
+        rw_out += rw_step;
+        st_out += st_step;
     }
 
     // ---- car state: written once ----
