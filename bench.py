@@ -660,11 +660,17 @@ def run_b200(args, rank, world):
         extra['config3'] = run_rollout_workload(args, quiet=True)
     peak, peak_kind = measured_peak()
     algo_step = ALGO_BYTES_PER_TRACK * B_TRACKS + ALGO_BYTES_PER_CAR * B_TRACKS * P_CARS
-    step_ms = ms / K
     n_calls = len(chunks)
+    step_ms = ms / K
     achieved = algo_step / (step_ms * 1e-3) / 1e9
-    traffic = ncu_traffic()
     fused = reps[0].plan(chunks[0]).launches == 1
+    traffic = ncu_traffic().get('race_rollout_fused_kernel' if fused else 'race_step_packed_kernel', {})
+    clk = sampler.summary()
+    sm_hz = 1e6 * float(clk.get('sm_mhz') or clk.get('sm_max_mhz') or 1965)
+    n_smsp = 4 * torch.cuda.get_device_properties(device).multi_processor_count
+    ipc = None
+    if traffic.get('warp_instructions_per_car_step') and args.variant == 'fast' and B_TRACKS == 4096:
+        ipc = traffic['warp_instructions_per_car_step'] * B_TRACKS * P_CARS / (n_smsp * sm_hz * step_ms * 1e-3)
     line = {
         'metric': METRIC, 'value': value, 'unit': 'env-steps/s',
         'n_gpus': world, 'steps': K, 'warmup': args.warmup, 'ms_per_step': step_ms,
@@ -686,7 +692,15 @@ def run_b200(args, rank, world):
                    'parallelism': 'dp%d (tracks sharded)' % world,
                    'host_cores_rank0': sorted(numa_cores) if numa_cores else 'unchanged'},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': traffic.get('dram_bytes_per_launch'), 'traffic_note': traffic.get('note'), 'peak_source': peak_kind,
+                     'traffic': traffic.get('dram_bytes_per_launch') if traffic.get('steps_per_launch') == (chunks[0] if fused else 1) else None,
+                     'traffic_note': traffic.get('source'), 'peak_source': peak_kind,
+                     # what actually bounds the kernel: instruction issue.  ncu's instruction count per
+                     # car-step x the cars of a step / (SM sub-partitions x clock x measured step time) = issue slots used
+                     'issue': None if ipc is None else {
+                         'bound': 'instruction issue (1 warp instruction per cycle and SM sub-partition)', 'achieved': ipc,
+                         'peak': 1.0, 'unit': 'warp instructions / cycle / sub-partition', 'frac': ipc,
+                         'warp_instructions_per_car_step': traffic['warp_instructions_per_car_step'],
+                         'sub_partitions': n_smsp, 'sm_mhz': sm_hz / 1e6},
                      'algorithmic_bytes_per_step': algo_step,
                      'algorithmic_bytes_per_launch': algo_step * chunks[0] if fused else algo_step,
                      'steps_per_launch': chunks[0] if fused else 1,
