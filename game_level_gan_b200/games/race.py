@@ -270,11 +270,12 @@ class Race(MultiEnvironment):
         from .rollout import HostStepper
         return HostStepper(self)
 
-    def host_rollout(self, T, chunk=25, mode='fused'):
+    def host_rollout(self, T, chunk=25, mode='fused', first_chunk=None):
         """A `HostRollout` (games/rollout.py) for this episode: T-step rollouts whose action tape and observations
-        live in pinned host memory, chunked and pipelined over copy-in / compute / copy-out streams."""
+        live in pinned host memory, chunked and pipelined over copy-in / compute / copy-out streams
+        (`run`, or `submit` / `wait` to overlap consecutive calls)."""
         from .rollout import HostRollout
-        return HostRollout(self, T, chunk, mode)
+        return HostRollout(self, T, chunk, mode, first_chunk)
 
     ROLLOUT_MODES = {'fused': _lib.ROLLOUT_FUSED, 'chained': _lib.ROLLOUT_CHAINED, 'stepwise': _lib.ROLLOUT_STEPWISE}
 

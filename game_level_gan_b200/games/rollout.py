@@ -251,7 +251,7 @@ class HostRollout(object):
     Results are those of `Race.rollout(actions, keep_all=True)`; bound to one episode like `RolloutPlan`.
     """
 
-    def __init__(self, env, T, chunk=25, mode='fused'):
+    def __init__(self, env, T, chunk=25, mode='fused', first_chunk=None):
         if env.num_tracks is None or env.num_tracks == 0:
             raise GlgError('HostRollout needs a reset environment with at least one track')
         if T <= 0 or chunk <= 0:
@@ -265,7 +265,11 @@ class HostRollout(object):
         self.actions_d = torch.zeros((T, P, B), dtype=torch.int64, device=dev)
         self.states_d = torch.empty((T, P, B, O + 2), dtype=torch.float32, device=dev)
         self.rewards_d = torch.empty((T, P, B), dtype=torch.float32, device=dev)
-        self.bounds = [(lo, min(lo + chunk, T)) for lo in range(0, T, chunk)]
+        # The copy-out of the observations is the slowest stage (721 KB per step of config 2 against ~8 us of kernel), so
+        # it should start early and then never wait: a short first chunk, full chunks after it.
+        first = max(1, chunk // 5) if first_chunk is None else max(1, int(first_chunk))
+        cuts = [0] + list(range(min(first, T), T, chunk)) + [T]
+        self.bounds = [(lo, hi) for lo, hi in zip(cuts[:-1], cuts[1:]) if hi > lo]
         self.plans = [env.rollout_plan(self.actions_d[lo:hi], keep_all=True, mode=mode,
                                        out=(self.states_d[lo:hi], self.rewards_d[lo:hi])) for lo, hi in self.bounds]
         self.launches = sum(p.launches for p in self.plans)
@@ -274,26 +278,35 @@ class HostRollout(object):
         self.ev_done = [torch.cuda.Event() for _ in self.bounds]
         self.h2d_bytes = self.actions_h.numel() * 8
         self.d2h_bytes = (self.states_h.numel() + self.rewards_h.numel()) * 4
+        self._pending = False
 
-    def run(self, actions=None):
-        """actions: [T,P,B] integer CPU tensor / numpy array (copied into the pinned staging buffer), or None when the
-        caller filled `self.actions_h` itself.  -> (states [T,P,B,O+2], rewards [T,P,B]): pinned host tensors, complete
-        when the call returns, overwritten by the next call."""
+    def submit(self, actions=None):
+        """Enqueue one rollout (copies in, kernels, copies out) and return without waiting; `wait()` returns the
+        results.  `actions`: [T,P,B] integer CPU tensor / numpy array - a pinned, contiguous int64 tensor is read by the
+        copy engine where it lies (it must stay unchanged until `wait()`), anything else goes through this object's pinned
+        staging buffer; None = the caller filled `self.actions_h`.  Two `HostRollout`s of one environment used alternately overlap the host's work on call i+1 (and its
+        reading of call i's results) with the device's work on call i - each owns its staging buffers and streams; the
+        kernels of all calls run in order on the caller's stream, so the episode advances exactly as with `run`."""
         env = self.env
         if env._epoch != self.epoch:
             raise GlgError('the environment was reset after this HostRollout was created - make a new one')
+        if self._pending:
+            raise GlgError('HostRollout.submit: the previous call has not been waited for')
+        src = self.actions_h
         if actions is not None:
-            a = actions.numpy() if torch.is_tensor(actions) else np.asarray(actions)
-            if tuple(a.shape) != tuple(self.actions_h.shape):
+            if tuple(actions.shape) != tuple(self.actions_h.shape):
                 raise ValueError('actions must have shape [T, num_players, num_boards] = %s' % (tuple(self.actions_h.shape),))
-            np.copyto(self.actions_h.numpy(), a, casting='unsafe')
+            if (torch.is_tensor(actions) and actions.dtype == torch.int64 and actions.is_contiguous()
+                    and not actions.is_cuda and actions.is_pinned()):
+                src = actions                          # already pinned int64: copied to the device straight from it
+            else:
+                a = actions.numpy() if torch.is_tensor(actions) else np.asarray(actions)
+                np.copyto(self.actions_h.numpy(), a, casting='unsafe')
         main = torch.cuda.current_stream(env.device)
-        self.s_in.wait_stream(main)                        # the staging buffers may still be read by the previous call
-        self.s_out.wait_stream(main)
         with torch.no_grad():
             for c, (lo, hi) in enumerate(self.bounds):
                 with torch.cuda.stream(self.s_in):
-                    self.actions_d[lo:hi].copy_(self.actions_h[lo:hi], non_blocking=True)
+                    self.actions_d[lo:hi].copy_(src[lo:hi], non_blocking=True)
                     self.ev_in[c].record(self.s_in)
             for c, (lo, hi) in enumerate(self.bounds):
                 main.wait_event(self.ev_in[c])
@@ -303,6 +316,20 @@ class HostRollout(object):
                     self.s_out.wait_event(self.ev_done[c])
                     self.states_h[lo:hi].copy_(self.states_d[lo:hi], non_blocking=True)
                     self.rewards_h[lo:hi].copy_(self.rewards_d[lo:hi], non_blocking=True)
-        main.wait_stream(self.s_out)
-        main.synchronize()
+        self._pending = True
+        return self
+
+    def wait(self):
+        """-> (states [T,P,B,O+2], rewards [T,P,B]) of the submitted call: pinned host tensors, complete on return,
+        overwritten by this object's next call."""
+        if not self._pending:
+            raise GlgError('HostRollout.wait: nothing was submitted')
+        self.s_out.synchronize()                           # the copies out are the last thing a call does
+        self._pending = False
         return self.states_h, self.rewards_h
+
+    def run(self, actions=None):
+        """actions: [T,P,B] integer CPU tensor / numpy array (copied into the pinned staging buffer), or None when the
+        caller filled `self.actions_h` itself.  -> (states [T,P,B,O+2], rewards [T,P,B]): pinned host tensors, complete
+        when the call returns, overwritten by the next call.  (`submit` + `wait`.)"""
+        return self.submit(actions).wait()

@@ -241,7 +241,9 @@ def test_host_rollout_equals_device_rollout(T, chunk):
     ref_s, ref_r = torch.stack([s for s, _ in ref]), torch.stack([r for _, r in ref])
     snap = b.snapshot()
     hr = b.host_rollout(T, chunk=chunk)
-    assert hr.launches == len(hr.bounds) == -(-T // chunk)
+    assert hr.launches == len(hr.bounds) and hr.bounds[0][0] == 0 and hr.bounds[-1][1] == T
+    assert all(a[1] == b[0] for a, b in zip(hr.bounds[:-1], hr.bounds[1:]))            # the chunks tile [0, T)
+    assert hr.bounds[0][1] == min(T, max(1, chunk // 5)) and all(hi - lo <= chunk for lo, hi in hr.bounds)
     assert hr.h2d_bytes == T * 2 * 300 * 8 and hr.d2h_bytes == T * 2 * 300 * 21 * 4
     for rep in range(2):
         st, rw = hr.run(acts if rep == 0 else acts.numpy())
@@ -256,3 +258,40 @@ def test_host_rollout_equals_device_rollout(T, chunk):
     b.reset(tracks)
     with pytest.raises(Exception):
         hr.run(acts)
+
+
+def test_host_rollouts_submitted_alternately_advance_one_episode():
+    """Two HostRollouts of one environment used in turn (`submit` the next call before `wait`ing for the previous one):
+    the kernels of all calls run in order, so four 15-step calls equal 60 per-step calls of the literal kernel."""
+    from game_level_gan_b200.games import Race, RaceConfig
+    tracks, g = _iid9(200, 92)
+    T, calls = 15, 4
+    acts = torch.randint(0, 9, (calls * T, 2, 200), generator=g)
+    acts = torch.where(torch.rand(acts.shape, generator=g) < 0.6, torch.ones_like(acts), acts)
+    a = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False, variant='brute')
+    b = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
+    a.reset(tracks)
+    b.reset(tracks)
+    ref = [a.step(acts[s].cuda()) for s in range(calls * T)]
+    ref_s, ref_r = torch.stack([s for s, _ in ref]), torch.stack([r for _, r in ref])
+    hrs = [b.host_rollout(T, chunk=6), b.host_rollout(T, chunk=6)]
+    got_s, got_r, pending = [], [], None
+    for i in range(calls):
+        h = hrs[i % 2]
+        h.submit(acts[i * T:(i + 1) * T])
+        if pending is not None:
+            st, rw = pending.wait()
+            got_s.append(st.clone())
+            got_r.append(rw.clone())
+        pending = h
+    st, rw = pending.wait()
+    got_s.append(st.clone())
+    got_r.append(rw.clone())
+    assert eq(torch.cat(got_s), ref_s) and eq(torch.cat(got_r), ref_r)
+    assert b.steps == a.steps and eq(b.positions, a.positions) and eq(b.scores, a.scores)
+    with pytest.raises(Exception):
+        hrs[0].wait()                                  # nothing pending
+    hrs[0].submit(acts[:T])
+    with pytest.raises(Exception):
+        hrs[0].submit(acts[:T])                        # not waited for
+    hrs[0].wait()
