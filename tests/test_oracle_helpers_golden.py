@@ -52,3 +52,34 @@ def test_predicates(g):
     c = [int(ho.segment_intersect(q[0], q[1], q[2], q[3])) for q in g['K_pts']]
     assert np.array_equal(o, g['K_orient']) and np.array_equal(c, g['K_cross'])
     assert (g['K_orient'] == 0).sum() > 20                      # the degenerate cases are in there
+
+
+def test_restatement_against_the_compiled_reference_live():
+    """Where oracle/_ref/libgame_ref.so exists (built by oracle/build_ref.py from the reference's own C++; it travels with
+    the working tree), drive it and the restatement side by side on fresh random jumps - not only the committed vectors."""
+    import ctypes
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    path = os.path.join(os.path.dirname(here), 'oracle', '_ref', 'libgame_ref.so')
+    if not os.path.exists(path):
+        pytest.skip('oracle/_ref/libgame_ref.so not built (python oracle/build_ref.py in the build container)')
+    sys.path.insert(0, os.path.join(here, 'golden'))
+    from make_golden_helpers import RefGame
+    lib = ctypes.CDLL(path)
+    z = np.load(os.path.join(GOLDEN, 'race_iid9.npz'))
+    left, right, centre = z['left'][4:10], z['right'][4:10], z['centre'][4:10]
+    rng = np.random.default_rng(123)
+    P, K = 2, 12
+    ref = RefGame(lib, left, right, P)
+    orc = ho.GameOracle(left, right, P)
+    prog = np.zeros(K, dtype=np.int64)
+    for s in range(40):
+        prog = np.clip(prog + rng.integers(-3, 6, K), -1, centre.shape[1] - 1)
+        trk = np.arange(K) // P
+        base = np.where(prog[:, None] >= 0, centre[trk, np.maximum(prog, 0)], np.array([[0., -0.3]]))
+        rows = (base + 0.3 * rng.standard_normal((K, 2))).astype(np.float32)
+        sel = np.nonzero(rng.random(K) < 0.8)[0]
+        d, f = ref.update(sel, rows[sel])
+        od, of = orc.update_players(list(sel), rows[sel])
+        assert np.array_equal(d, od) and np.array_equal(f, of), 'step %d' % s
+    ref.close()
