@@ -776,6 +776,28 @@ class LstmAgents(object):
         return torch.stack(acts, 0)
 
 
+def stock_agents(P):
+    """The reference's own agents for config 3 - `PPOAgent(9, LSTMPolicy(20, 9))` with the shipped weights
+    `learned/agent_{i}_0.pt` (train-gan.py:40-50) - when baseline/_ref holds them (tools/make_baseline_ref.py), else None."""
+    root = os.path.join(ROOT, 'baseline', '_ref')
+    paths = [os.path.join(root, 'learned', 'agent_%d_0.pt' % i) for i in range(P)]
+    if not (os.path.isdir(os.path.join(root, 'agents')) and all(os.path.exists(p) for p in paths)):
+        return None
+    try:
+        with stdout_to_stderr():
+            if root not in sys.path:
+                sys.path.insert(0, root)
+            from agents import PPOAgent
+            from policies import LSTMPolicy
+            agents = [PPOAgent(9, LSTMPolicy(20, 9)) for _ in range(P)]
+            for a, p in zip(agents, paths):
+                a.load(p)
+        return agents
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write('stock agents unavailable (%s: %s), using stand-in LSTM agents\n' % (type(e).__name__, e))
+        return None
+
+
 def run_rollout_workload(args, quiet=False):
     """train-gan.py:86-104 on synthetic boards: reset, play the episode with 2 LSTM agents, winner statistics.
     Compares the reference-style per-step loop with GraphedRollout."""
@@ -783,21 +805,37 @@ def run_rollout_workload(args, quiet=False):
     device = torch.device('cuda', torch.cuda.current_device())
     B, T_limit = 2060, 500                                          # (1024 generated + 6 predefined) x 2 mirrored
     tracks = synthetic_tracks(B, SEED)
+    from game_level_gan_b200.games import capture_safe_agents
     out = {'workload': 'config3: episode rollout, %d boards x 2 LSTM(256x2) agents, <= %d steps' % (B, T_limit)}
     with torch.no_grad():
         for mode in ('loop', 'graph'):
             env = Race(timeout=T_limit / 20. - 0.025, cars=RaceConfig.cars, framerate=1. / 20., log_history=False, device=device)
-            agents = LstmAgents(2, B, device)
+            stock = stock_agents(2)
+            if stock is not None:
+                # the reference's loop body, train-gan.py:92 / 95-96 (Gumbel sampling as shipped)
+                out['agents'] = 'stock PPOAgent(LSTMPolicy(20, 9)) with the shipped weights learned/agent_{0,1}_0.pt, act(training=False)'
+                if mode == 'graph':
+                    act, reset_agents = capture_safe_agents(stock)
+                else:
+                    act = lambda st: torch.stack([a.act(s, training=False) for a, s in zip(stock, st)], dim=0)
+
+                    def reset_agents():
+                        for a in stock:
+                            a.reset()
+            else:
+                out['agents'] = 'stand-in LSTMPolicy-shaped networks, random weights (baseline/_ref has no agents)'
+                agents = LstmAgents(2, B, device)
+                act, reset_agents = agents, agents.reset
             best = None
             for rep in range(2 if quiet else 3):
                 states, any_valid = env.reset(tracks)
-                agents.reset()
-                roll = GraphedRollout(env, agents, steps_per_replay=16, on_reset=agents.reset).capture() if mode == 'graph' else None
+                reset_agents()
+                roll = GraphedRollout(env, act, steps_per_replay=16, on_reset=reset_agents).capture() if mode == 'graph' else None
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 if mode == 'loop':
                     while any_valid and not env.finished():
-                        states, rewards = env.step(agents(states))
+                        states, rewards = env.step(act(states))
                 else:
                     roll.run(states)
                 stats = env.winner_stats(1)

@@ -28,7 +28,9 @@ def main():
     for pkg in ('games', 'utils', 'agents', 'policies'):      # agents / policies: tests/test_rollout_graph_gpu.py (PPOAgent.act)
         shutil.copytree(os.path.join(src, pkg), os.path.join(dst, pkg),
                         ignore=shutil.ignore_patterns('__pycache__', '*.pyc'))
-    print('copied %s/{games,utils,agents,policies} -> %s' % (src, dst))
+    if os.path.isdir(os.path.join(src, 'learned')):         # the shipped agents (train-gan.py:22, 46-50): config 3 of bench.py
+        shutil.copytree(os.path.join(src, 'learned'), os.path.join(dst, 'learned'))
+    print('copied %s/{games,utils,agents,policies,learned} -> %s' % (src, dst))
 
 
 if __name__ == '__main__':
