@@ -441,6 +441,30 @@ def run_config4(args, rank, world, device, barrier, total_tracks, trials=4, T=20
     return out
 
 
+def run_reset(device, variant):
+    """`Race.reset` of config 2 (4096 tracks from float [B,L,2] and from 4-bit generator levels): geometry, validity
+    (games/race.py:126-211, 326-334), extents, car state and the noop step - device time per call, median of 7."""
+    from game_level_gan_b200.games import Race, RaceConfig
+    env = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False, device=device, variant=variant)
+    tracks = synthetic_tracks(B_TRACKS, SEED + 5).to(device)
+    levels = torch.round(tracks[:, :, 0] * 4 + 4).to(torch.uint8)
+    out = {'workload': 'Race.reset of %d tracks x %d cars (track build + validity + extents + init + noop step)' % (B_TRACKS, P_CARS)}
+    for name, call in (('reset_us', lambda: env.reset(tracks)), ('reset_levels_us', lambda: env.reset_levels(levels))):
+        times = []
+        for i in range(9):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            call()
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                times.append(1e3 * e0.elapsed_time(e1))
+        out[name] = median(times)
+    out['steps_worth'] = 'one reset = %.0f steps of the fused rollout at 8.6 us' % (out['reset_us'] / 8.6)
+    return out
+
+
 def run_config5(device, T=100):
     """Config 5: Pacman, 65 536 boards of 15x15, 2 players, random actions: step + observation per step."""
     import numpy as np
@@ -666,6 +690,7 @@ def run_b200(args, rank, world):
         return
     if world == 1 and not args.no_extra:
         extra['config5'] = run_config5(device)
+        extra['reset'] = run_reset(device, args.variant)
         extra['config3'] = run_rollout_workload(args, quiet=True)
     peak, peak_kind = measured_peak()
     algo_step = ALGO_BYTES_PER_TRACK * B_TRACKS + ALGO_BYTES_PER_CAR * B_TRACKS * P_CARS

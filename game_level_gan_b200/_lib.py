@@ -49,6 +49,7 @@ SYMBOLS = {
     'glg_track_build': (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     'glg_track_build_levels': (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     'glg_track_validate': (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp]),
+    'glg_track_validate_pairs': (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp]),
     'glg_track_extent': (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp]),
     'glg_race_init': (ctypes.c_int, [RaceState, _i32, _i32, _vp, _vp]),
     'glg_race_step': (ctypes.c_int, [ctypes.POINTER(RaceParams), _vp, _i32, _i32, _vp, _vp, _vp, RaceState,

@@ -151,6 +151,106 @@ __global__ void track_validate_kernel(const float* __restrict__ geom, int B, int
     if (threadIdx.x == 0) valid[b] = bad_flag ? 0 : 1;
 }
 
+// Same result from the SIGN MATRIX.  The 2N lines of a track are the consecutive pairs of the cyclic polyline
+// c[0..2N) = right[N-1] ... right[0], left[0] ... left[N-1] (walls; start line = (c[N-1], c[N]); finish line =
+// (c[2N-1], c[0])), and the reference's o1..o4 of a pair of lines are the orientation of an END POINT of one line with
+// respect to the other (games/race.py:230-238, 252-255).  End points are shared by neighbouring lines, so the
+// 4 x 33 670 orientation values of the pair loop are only 2N x 2N distinct ones: S[i][v] = sign of line i (in the
+// reference's p -> q order) against vertex v, the same separately rounded arithmetic.  Phase 1 evaluates them once, 32
+// vertices per warp instruction, and keeps two bit rows per line (negative, positive).  Line j "straddles" line i when
+// S[i][.] is strictly negative at one end point of j and strictly positive at the other - (o1*o2 < 0) - which for
+// consecutive vertices is a shift and two ANDs of the bit rows; the track is invalid iff some pair straddles each other.
+// Half the arithmetic of the pair loop and none of its sign conversions; results identical (tests/test_race_gpu.py).
+constexpr int VB_THREADS = 128;
+__host__ __device__ inline int vb_words(int N) { return (2 * N + 31) >> 5; }
+__host__ __device__ inline size_t vb_smem(int N) {      // xs, ys [2N] f32; neg / pos bit rows [2N][W] u32
+    return (size_t)2 * N * 8 + (size_t)2 * N * vb_words(N) * 8;
+}
+
+template <int WMAX>
+__global__ void __launch_bounds__(VB_THREADS) track_validate_bits_kernel(const float* __restrict__ geom, int B, int N,
+                                                                         uint8_t* __restrict__ valid)
+{
+    extern __shared__ __align__(16) unsigned char vb_raw[];
+    __shared__ int bad_flag;
+    const int b = blockIdx.x, V = 2 * N, W = vb_words(N);
+    float* xs = reinterpret_cast<float*>(vb_raw);
+    float* ys = xs + V;
+    unsigned* neg = reinterpret_cast<unsigned*>(ys + V);
+    unsigned* pos = neg + V * W;
+    const float2* rec = reinterpret_cast<const float2*>(geom) + (size_t)b * 3 * N;
+    if (threadIdx.x == 0) bad_flag = 0;
+    for (int v = threadIdx.x; v < V; v += VB_THREADS) {
+        const float2 pt = rec[v];
+        xs[v] = pt.x;
+        ys[v] = pt.y;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // phase 1: line i = (c[i], c[i+1 mod V]); right walls and the start line run from c[i+1] to c[i] in the reference.
+    // A lane tests the same vertices (lane, lane + 32, ...) against every line: they stay in registers.
+    float vx[WMAX], vy[WMAX];
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w) {
+        const int v = 32 * w + lane;
+        vx[w] = v < V ? xs[v] : 0.f;
+        vy[w] = v < V ? ys[v] : 0.f;
+    }
+    for (int i = warp; i < V; i += VB_THREADS / 32) {
+        const int i1 = i + 1 == V ? 0 : i + 1;
+        const bool rev = i < N;
+        const float px = xs[rev ? i1 : i], py = ys[rev ? i1 : i], qx = xs[rev ? i : i1], qy = ys[rev ? i : i1];
+        const float ax = xsub(qx, px), ay = xsub(qy, py);                      // q - p
+        unsigned mine_n = 0, mine_p = 0;                                       // lane w keeps word w of the two rows
+#pragma unroll
+        for (int w = 0; w < WMAX; ++w) {
+            const bool in = 32 * w + lane < V;
+            const float val = det2(ay, xsub(vx[w], qx), ax, xsub(vy[w], qy));  // race.py:238 with r = c[32w + lane]
+            const unsigned nb = __ballot_sync(FULL, in && val < 0.f), pb = __ballot_sync(FULL, in && val > 0.f);
+            if (lane == w) { mine_n = nb; mine_p = pb; }
+        }
+        if (lane < W) { neg[i * W + lane] = mine_n; pos[i * W + lane] = mine_p; }
+    }
+    __syncthreads();
+    // phase 2a: straddle rows (bit j of row i: line j has its end points strictly on different sides of line i),
+    // written over the `neg` rows - every (row, word) is read and written by one thread, words w and w+1 of a row
+    // are needed, so a row is handled by one thread
+    for (int i = threadIdx.x; i < V; i += VB_THREADS) {
+        unsigned* nr = neg + i * W;
+        const unsigned* pr_ = pos + i * W;
+        const unsigned n0 = nr[0], p0 = pr_[0];
+        unsigned ncur = n0, pcur = p0;
+        for (int w = 0; w < W; ++w) {
+            const bool last = w == W - 1;
+            const unsigned nnext = last ? n0 : nr[w + 1], pnext = last ? p0 : pr_[w + 1];
+            // successor bits: vertex 32w+b+1; in the last word the successor of vertex V-1 is vertex 0
+            unsigned ns = (ncur >> 1) | (nnext << 31), ps = (pcur >> 1) | (pnext << 31);
+            if (last) {
+                const int top = (V - 1) & 31;                                   // bit of vertex V-1 in the last word
+                ns = (ncur >> 1) | ((n0 & 1u) << top);
+                ps = (pcur >> 1) | ((p0 & 1u) << top);
+            }
+            nr[w] = (ncur & ps) | (pcur & ns);
+            ncur = nnext;
+            pcur = pnext;
+        }
+    }
+    __syncthreads();
+    // phase 2b: sparse - few lines straddle a given line
+    for (int i = threadIdx.x; i < V; i += VB_THREADS) {
+        for (int w = 0; w < W; ++w) {
+            unsigned m = neg[i * W + w];
+            while (m) {
+                const int j = 32 * w + __ffs(m) - 1;
+                m &= m - 1;
+                if ((neg[j * W + (i >> 5)] >> (i & 31)) & 1u) bad_flag = 1;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) valid[b] = bad_flag ? 0 : 1;
+}
+
 // One warp per track: extent[b] = { max |point| over the record, max wall length of the polyline except the start line },
 // both rounded UP (they are used as conservative bounds).  A record with a non-finite coordinate
 // gets +inf / +inf, which makes every car of that track take the unpruned path.
@@ -239,9 +339,26 @@ extern "C" int glg_track_validate(const float* geom, int32_t B, int32_t N, uint8
     GLG_REQUIRE(B >= 0 && N >= 2 && N <= 512, "glg_track_validate: need B >= 0 and 2 <= N <= 512 (got B=%d N=%d)", B, N);
     GLG_REQUIRE((B == 0) || (geom && valid), "glg_track_validate: null pointer");
     if (B == 0) return GLG_OK;
+    if (vb_smem(N) <= 48 * 1024) {                       // N <= 210: the sign-matrix kernel
+        if (vb_words(N) <= 9)                            // N <= 144 (the reference's N = 130: 9 words per bit row)
+            track_validate_bits_kernel<9><<<B, VB_THREADS, vb_smem(N), (cudaStream_t)stream>>>(geom, B, N, valid);
+        else
+            track_validate_bits_kernel<14><<<B, VB_THREADS, vb_smem(N), (cudaStream_t)stream>>>(geom, B, N, valid);
+        return launch_status("glg_track_validate");
+    }
+    return glg_track_validate_pairs(geom, B, N, valid, stream);
+}
+
+extern "C" int glg_track_validate_pairs(const float* geom, int32_t B, int32_t N, uint8_t* valid,
+                                        glg_stream_t stream)
+{
+    using namespace glg;
+    GLG_REQUIRE(B >= 0 && N >= 2 && N <= 512, "glg_track_validate_pairs: need B >= 0 and 2 <= N <= 512 (got B=%d N=%d)", B, N);
+    GLG_REQUIRE((B == 0) || (geom && valid), "glg_track_validate_pairs: null pointer");
+    if (B == 0) return GLG_OK;
     const int M = 2 * (N - 1) + 2;
     int threads = ((M / 2 + 31) / 32) * 32;
     if (threads > 1024) threads = 1024;
     track_validate_kernel<<<B, threads, (size_t)M * sizeof(float4), (cudaStream_t)stream>>>(geom, B, N, valid);
-    return launch_status("glg_track_validate");
+    return launch_status("glg_track_validate_pairs");
 }

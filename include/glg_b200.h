@@ -122,6 +122,10 @@ int glg_track_build_levels(const uint8_t* levels, int32_t B, int32_t L,
  * Replaces Race._is_correct, games/race.py:326-334 (IMPL_GPU branch of reset, :199-200).
  *   valid [B] u8 out                                                                         */
 int glg_track_validate(const float* geom, int32_t B, int32_t N, uint8_t* valid, glg_stream_t stream);
+/* The same through the literal loop over all pairs of lines (the reference's own shape of the computation,
+ * games/race.py:252-255 on every pair); glg_track_validate uses it for N > 210 and otherwise evaluates each
+ * (line, end point) orientation once (neighbouring lines share end points) - identical results, kept as a cross-check. */
+int glg_track_validate_pairs(const float* geom, int32_t B, int32_t N, uint8_t* valid, glg_stream_t stream);
 
 /* Conservative per-track bounds the production step kernel prunes with (no reference counterpart):
  *   extent [B,2] f32 out = { max |point| over the record, longest wall of the polyline (the start

@@ -402,3 +402,33 @@ def test_wide_and_wild_float_tracks_all_variants():
     for v in ('fast', 'warp', 'scan'):
         assert eq(envs[v].positions, ref.positions) and eq(envs[v].scores, ref.scores) and eq(envs[v].winners(), ref.winners())
     assert 0 < int(ref.alive.sum()) or int(ref._valid_tracks.sum()) >= 0
+
+
+@pytest.mark.parametrize('L', [128, 64, 200, 208, 30, 3])
+def test_validity_sign_matrix_equals_the_pair_loop(L):
+    """glg_track_validate (every (line, end point) orientation once, bit rows) against glg_track_validate_pairs (the
+    literal loop over all pairs of lines, games/race.py:326-334): curly iid-9 tracks (many self-crossings), gentle and
+    straight ones (collinear walls: orientation values that are exactly or almost zero), float widths."""
+    from game_level_gan_b200 import _lib
+    from game_level_gan_b200._lib import check, ptr
+    from game_level_gan_b200.games import Race, RaceConfig
+    g = torch.Generator().manual_seed(900 + L)
+    B = 600
+    tracks = torch.zeros(B, L, 2)
+    tracks[:, :, 0] = torch.linspace(-1., 1., 9)[torch.randint(0, 9, (B, L), generator=g)]
+    tracks[100:200, :, 0] *= 0.25                                              # gentle
+    tracks[200:260, :, 0] = 0.                                                 # straight: every wall collinear
+    tracks[260:330, :, 0] = torch.where(torch.rand((70, L), generator=g) < 0.8, torch.zeros(70, L), tracks[260:330, :, 0])
+    tracks[330:450, :, 0] = torch.rand((120, L), generator=g) * 2 - 1
+    tracks[330:450, :, 1] = torch.rand((120, L), generator=g)
+    env = Race(timeout=40., cars=RaceConfig.cars, framerate=1. / 20., log_history=False)
+    env.reset(tracks)
+    N = L + 2
+    a = torch.empty(B, dtype=torch.uint8, device='cuda')
+    b = torch.empty(B, dtype=torch.uint8, device='cuda')
+    stream = _lib.stream_ptr(env.device)
+    check(_lib.lib().glg_track_validate(ptr(env._geom), B, N, ptr(a), stream), 'glg_track_validate')
+    check(_lib.lib().glg_track_validate_pairs(ptr(env._geom), B, N, ptr(b), stream), 'glg_track_validate_pairs')
+    assert eq(a, b) and eq(a, env._valid_tracks)
+    if L >= 30:
+        assert 0 < int(a.sum()) < B                                            # both outcomes occur
