@@ -58,6 +58,56 @@ def test_config2_full_size_vs_c_oracle():
     assert eq(env.winners(), orc.winners())
 
 
+def test_config2_full_size_100_step_fused_rollout_vs_c_oracle():
+    """The bench's production path at the bench's size: ONE fused launch plays 100 steps of 4096 tracks x 2 cars
+    (`north_star`: 100-step rollouts must be checked); every observation and reward of every step and the final car
+    state against the C oracle, bit for bit.  A second rollout continues the episode through the time when cars die and
+    finish."""
+    from game_level_gan_b200.games import Race, RaceCar, _tables
+    g = torch.Generator().manual_seed(4048)
+    B, P, T = 4096, 2, 100
+    tracks = iid9_tracks(B, g)
+    # an action tape on which most cars survive (uniformly random actions kill every car within ~100 steps, and then the
+    # reference returns 19-wide zeros): a wall-avoiding driver plays the episode once, closed loop, 10 % random actions
+    drv = Race(timeout=40., cars=[RaceCar(*c) for c in CARS4[:P]], framerate=1. / 20., log_history=False)
+    obs, _ = drv.reset(tracks)
+    gd = torch.Generator(device='cuda').manual_seed(7)
+    tape = []
+    for _ in range(2 * T):
+        left, right = obs[..., 7] + obs[..., 8] + 0.5 * obs[..., 6], obs[..., 10] + obs[..., 11] + 0.5 * obs[..., 12]
+        steer = torch.zeros(obs.shape[:2], dtype=torch.int64, device='cuda')
+        steer[right > left + 0.02] = 1
+        steer[left > right + 0.02] = 2
+        thr = torch.where(obs[..., 18] > 0.05, 0, 1)
+        a = steer * 3 + thr
+        rnd = torch.rand(a.shape, generator=gd, device='cuda') < 0.1
+        a = torch.where(rnd, torch.randint(0, 9, a.shape, generator=gd, device='cuda'), a)
+        tape.append(a)
+        obs, _ = drv.step(a)
+    acts = torch.stack(tape).cpu()
+    orc = c_oracle(CARS4[:P])
+    st, ct, _ = _tables.heading_tables(128)
+    so, _ = orc.reset(tracks.numpy(), st.numpy(), ct.numpy())
+    env = Race(timeout=40., cars=[RaceCar(*c) for c in CARS4[:P]], framerate=1. / 20., log_history=False)
+    s0, _ = env.reset(tracks)
+    assert nmismatch(s0, so) == 0
+    for half in range(2):
+        a = acts[half * T:(half + 1) * T]
+        plan = env.rollout_plan(a.cuda(), keep_all=True, mode='fused')
+        assert plan.launches == 1
+        sg, rg = plan.run()
+        sg, rg = sg.cpu(), rg.cpu()
+        bad = 0
+        for s in range(T):
+            so, ro_ = orc.step(a[s].numpy())
+            bad += nmismatch(sg[s], so) + nmismatch(rg[s], ro_)
+        bad += nmismatch(env.positions, orc.pos) + nmismatch(env.directions, orc.dir) + nmismatch(env.speeds, orc.speed)
+        bad += nmismatch(env._alive, orc.alive) + nmismatch(env._finishes, orc.finishes) + nmismatch(env.scores, orc.scores)
+        assert bad == 0, 'rollout %d' % half
+    assert eq(env.winners(), orc.winners())
+    assert 0 < int(env._alive.sum()) < B * P and int(env._alive.sum()) > B     # most cars drove the 200 steps, some died
+
+
 def test_config4_shard_is_a_gather_of_a_small_batch():
     """131 072 tracks x 4 cars (config 4 on 8 GPUs, per GPU) built by repeating 256 distinct tracks in a
     random order: all 524 288 cars must equal, bit for bit, the corresponding cars of the 256-track batch
