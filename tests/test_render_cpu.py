@@ -62,3 +62,36 @@ def test_pixel_transform_follows_the_reference_formula():
     for k, (x, y) in enumerate(b.view(-1, 2)):
         assert px[k, 0] == int(0.05 * 256 + 0.9 * 256 * ((x - minx) / longer + shiftx))
         assert px[k, 1] == 256 - int(0.05 * 256 + 0.9 * 256 * ((y - miny) / longer + shifty))
+
+
+def test_prettier_tracks_svg_with_a_stand_in_svgwrite(monkeypatch):
+    """`svgwrite` is not installed here (the reference imports it inside the method too): a stand-in module records the
+    polygons - 129 tarmac quads in two alternating greys (bands of 5) and the 2 x 7 chequered finish strip per board,
+    all inside the padded canvas."""
+    import sys
+    import types
+    from game_level_gan_b200.games import race_render
+
+    class Drawing(object):
+        def __init__(self, **kw):
+            self.kw, self.items = kw, []
+
+        def polygon(self, points, fill):
+            return ('polygon', points, fill)
+
+        def add(self, item):
+            self.items.append(item)
+
+    fake = types.ModuleType('svgwrite')
+    fake.Drawing = Drawing
+    fake.rgb = lambda r, g, b: 'rgb(%d,%d,%d)' % (r, g, b)
+    monkeypatch.setitem(sys.modules, 'svgwrite', fake)
+    imgs = race_render.prettier_tracks_svg(Boards(load_case('iid9'), 2), top_n=2, size=512, pad=0.05)
+    assert len(imgs) == 2 and imgs[0].kw == {'shape_rendering': 'crispEdges'}
+    for d in imgs:
+        assert len(d.items) == 129 + 14
+        quads, cells = d.items[:129], d.items[129:]
+        assert [q[2] for q in quads[:11]] == ['rgb(70,70,70)'] * 5 + ['rgb(50,50,50)'] * 5 + ['rgb(70,70,70)']
+        assert sorted(set(c[2] for c in cells)) == ['rgb(20,20,20)', 'rgb(210,210,210)']
+        pts = np.array([p for it in d.items for p in it[1]])
+        assert pts.shape[1] == 2 and pts.min() > -0.03 * 512 and pts.max() < 1.03 * 512
