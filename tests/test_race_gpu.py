@@ -232,7 +232,8 @@ def test_reset_from_generator_levels():
 @pytest.mark.parametrize('P', [1, 3, 4, 8])
 def test_chained_rollout_other_player_counts(P):
     """Fused (one persistent kernel) and chained rollouts (LL hand-over with keep_all, release/acquire stamps
-    without) for 1, 3, 4 and 8 cars per track - an idle half warp, several warps per track - against per-step calls."""
+    without) for 1, 3, 4 and 8 cars per track - an idle half warp, several warps per track - against per-step calls,
+    which are themselves compared with the C oracle."""
     from game_level_gan_b200.games import Race, RaceCar
     cars = [RaceCar(*c) for c in [(60., 4., 40.), (60., 1., 80.), (80., 2., 60.), (50., 3., 50.), (70., 2., 30.),
                                   (40., 4., 90.), (90., 1., 45.), (55., 2., 70.)][:P]]
@@ -243,8 +244,25 @@ def test_chained_rollout_other_player_counts(P):
     acts = torch.randint(0, 9, (T, P, B), generator=g)
     acts = torch.where(torch.rand((T, P, B), generator=g) < 0.5, torch.ones_like(acts), acts)
     a = Race(timeout=40., cars=cars, framerate=1. / 20., log_history=False)
-    a.reset(tracks)
+    s0, _ = a.reset(tracks)
     per_step = [a.step(acts[s].cuda()) for s in range(T)]
+    # the per-step results themselves against the C oracle (pinned to the reference's fixtures, tests/test_oracle_c.py):
+    # the rollout modes below are then held to reference-equivalent values, not only to another CUDA path
+    import ctypes
+    from game_level_gan_b200.games import _tables
+    from oracle import c_oracle as co
+    cpr = co.RaceParams()
+    ctypes.memmove(ctypes.byref(cpr), ctypes.byref(_tables.race_params(cars, 1. / 20., 40., 18, 10.)), ctypes.sizeof(cpr))
+    orc = co.CRace(cpr)
+    st_, ct_, _ = _tables.heading_tables(128)
+    so, _ = orc.reset(tracks.numpy(), st_.numpy(), ct_.numpy())
+    assert eq(s0, so)
+    for s in range(T):
+        so, ro_ = orc.step(acts[s].numpy())
+        if so.shape[-1] != 20:                       # nobody alive any more: the reference's 19-wide early-out
+            break
+        assert eq(per_step[s][0], so) and eq(per_step[s][1], ro_), ('oracle', s)
+    assert s >= 20
     for keep_all, mode in ((True, 'fused'), (False, 'fused'), (True, 'chained'), (False, 'chained'), (True, 'stepwise')):
         b = Race(timeout=40., cars=cars, framerate=1. / 20., log_history=False)
         b.reset(tracks)
