@@ -1,5 +1,6 @@
 """GraphedRollout (one CUDA graph of k x [policy -> env step]) against the reference's per-step loop
-(train-gan.py:91-93) run with the same deterministic policies: the environment must end in the same state."""
+(train-gan.py:91-93) run with the same deterministic policies, and against the same loop with the C oracle as the
+environment: the environment must end in the same state."""
 import pytest
 import torch
 
@@ -72,6 +73,24 @@ def test_graphed_rollout_matches_the_reference_loop(timeout, k):
     assert eq(env.winners(), env2.winners())
     if timeout > 10:
         assert int(env.finishes.sum()) + int((~env.alive).sum()) > 0
+    # the same episode with the C ORACLE as the environment (pinned to the reference's fixtures) and a third instance
+    # of the policy: the closed loop ends in the same state, so the two CUDA loops above are reference-equivalent
+    import ctypes
+    from game_level_gan_b200.games import _tables
+    from oracle import c_oracle as co
+    cpr = co.RaceParams()
+    ctypes.memmove(ctypes.byref(cpr), ctypes.byref(_tables.race_params(RaceConfig.cars, 1. / 20., timeout, 18, 10.)), ctypes.sizeof(cpr))
+    orc = co.CRace(cpr)
+    st_, ct_, _ = _tables.heading_tables(128)
+    with torch.no_grad():
+        pol3 = RecurrentArgmaxPolicy(2, B, 20, seed=1)
+        so, any_valid = orc.reset(tracks.numpy(), st_.numpy(), ct_.numpy())
+        while any_valid and not orc.finished():
+            so, _ = orc.step(pol3(torch.from_numpy(so).cuda()).cpu().numpy())
+    assert orc.steps == env.steps
+    assert eq(env.positions, orc.pos) and eq(env.directions, orc.dir) and eq(env.speeds, orc.speed)
+    assert eq(env._alive, orc.alive) and eq(env._finishes, orc.finishes) and eq(env.scores, orc.scores)
+    assert eq(env.winners(), orc.winners())
 
 
 def test_host_stepper_matches_step():
