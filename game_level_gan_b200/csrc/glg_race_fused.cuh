@@ -173,9 +173,13 @@ __device__ __noinline__ bool fused_collide_all(const float* xs, const float* ys,
 #ifndef GLG_F_ACT_SMEM
 #define GLG_F_ACT_SMEM 1          // actions fetched 16 steps at a time by cp.async (0: one __ldg per step, a step ahead)
 #endif
+#ifndef GLG_F_S1_UNROLL
+#define GLG_F_S1_UNROLL 3         // stage-1 passes per loop trip (9 passes at N = 130)
+#endif
 #ifndef GLG_F_RAYTAB
 #define GLG_F_RAYTAB 1            // ray table in shared memory (0: per-lane indexed loads from the parameter bank)
 #endif
+constexpr int S1_UNROLL = GLG_F_S1_UNROLL;
 constexpr int FW = 16;                         // centre points in the arg-min window (one per lane of a group)
 constexpr int FW_BACK = 5;                     // of which behind the last arg-min (cars mostly advance)
 
@@ -440,7 +444,7 @@ race_rollout_fused_kernel(const __grid_constant__ glg_race_params pr, const Fuse
             unsigned sbits = 0, fbits = 0;
             const float2* xp = reinterpret_cast<const float2*>(xs) + gl;
             const float2* yp = reinterpret_cast<const float2*>(ys) + gl;
-#pragma unroll 3
+#pragma unroll S1_UNROLL
             for (int pass = 0; pass < npass; ++pass, xp += PK_G, yp += PK_G) {
                 // two consecutive vertices per lane; z = (u . nd) + i (u x nd); flags from Im z^9 (glg_sensors.cuh,
                 // scan_two_stage).  im3n = -Im z^3 and the bracket of the second cubing is negated too, so that no
